@@ -1,5 +1,6 @@
 // extern "C" operator-level entry points of libgvl.so (declared in include/gvl.h).
 #include "gvl_internal.h"
+#include "decode.h"
 #include "../../include/gvl.h"
 
 using namespace gvl;
@@ -82,6 +83,39 @@ int gvl_rope_qkv_cache(const void* qkv, void* q_out, void* k_cache, void* v_cach
     return rope_qkv_cache((const __nv_bfloat16*)qkv, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache,
                           (__nv_bfloat16*)v_cache, (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, positions,
                           tokens, heads, kv_heads, head_dim, pos0, max_ctx, S(stream));
+}
+
+int gvl_gemv_bf16(const void* x, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                  const void* norm_w, float norm_eps, const void* bias, const void* residual, int ldr, int act,
+                  int out_f32, void* stream) {
+    if (!x || !W || !out) return GVL_ERR_ARG;
+    return gemv_bf16((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)W, ldw, out, ldo, M, N, K,
+                     (const __nv_bfloat16*)norm_w, norm_eps, (const __nv_bfloat16*)bias,
+                     (const __nv_bfloat16*)residual, ldr, act, out_f32, S(stream));
+}
+size_t gvl_decode_attention_workspace(int heads, int head_dim, int max_ctx) {
+    return decode_attention_workspace(heads, head_dim, max_ctx);
+}
+int gvl_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* o, float* workspace,
+                         const int* ctx_len_dev, int heads, int kv_heads, int head_dim, int max_ctx, float scale,
+                         void* stream) {
+    if (!q || !k_cache || !v_cache || !o || !workspace || !ctx_len_dev) return GVL_ERR_ARG;
+    return decode_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache,
+                            (__nv_bfloat16*)o, workspace, ctx_len_dev, heads, kv_heads, head_dim, max_ctx, scale,
+                            S(stream));
+}
+int gvl_argmax_f32(const float* logits, int n, long long* out_token, void* stream) {
+    if (!logits || !out_token || n <= 0) return GVL_ERR_ARG;
+    return argmax_f32(logits, n, out_token, S(stream));
+}
+int gvl_visual_concat(const void* a, int a_rows, const void* b, int b_rows, const void* newline, void* out, int n_seg,
+                      int dim, void* stream) {
+    return visual_concat((const __nv_bfloat16*)a, a_rows, (const __nv_bfloat16*)b, b_rows,
+                         (const __nv_bfloat16*)newline, (__nv_bfloat16*)out, n_seg, dim, S(stream));
+}
+int gvl_layernorm_f32_out_f32(const float* x, const float* w, const float* b, float* y, int rows, int cols, float eps,
+                              void* stream) {
+    return layernorm_f32_to_f32(x, w, b, y, rows, cols, eps, S(stream));
 }
 
 }  // extern "C"

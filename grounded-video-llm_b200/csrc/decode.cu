@@ -1,0 +1,516 @@
+// Decode-side kernels (q_len = 1): everything here is HBM-bound weight / KV streaming, so the
+// design rules are coalesced 128-bit loads, many bytes in flight per SM and no tensor cores.
+//   gemv_kernel            y = W x for M<=4 rows of x, optional fused input RMSNorm, SwiGLU, residual, bias
+//   decode_attn_kernel     one query vs the KV cache, split along the context (flash-decoding style)
+//   decode_attn_combine    merge the per-split (max, sum, partial-output) triples
+//   argmax / token kernels greedy sampling + device-side step bookkeeping (so a step is graph-replayable)
+// Reference call sites: Phi3DecoderLayer.forward with q_len=1 (modeling_phi3.py:1034-1095, 629-775),
+// lm_head + .float() (modeling_phi3.py:1525-1526), HF greedy loop (llava_next_video.py:655-661).
+#include "gvl_internal.h"
+#include "ptx.cuh"
+#include "decode.h"
+
+namespace gvl {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float dot8(uint4 w, uint4 x) {
+    float2 a, b;
+    float s;
+    a = unpack_bf16(w.x); b = unpack_bf16(x.x); s = a.x * b.x + a.y * b.y;
+    a = unpack_bf16(w.y); b = unpack_bf16(x.y); s += a.x * b.x + a.y * b.y;
+    a = unpack_bf16(w.z); b = unpack_bf16(x.z); s += a.x * b.x + a.y * b.y;
+    a = unpack_bf16(w.w); b = unpack_bf16(x.w); s += a.x * b.x + a.y * b.y;
+    return s;
+}
+
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_MAXM = 4;
+
+// x rows are staged (and optionally RMS-normalised exactly like rmsnorm_bf16) in shared memory as bf16.
+// Each warp owns whole output rows; SWIGLU pairs the gate row and the up row of one output column.
+template <int MT, bool SWIGLU>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
+            void* __restrict__ out, int ldo, int N, int K, const __nv_bfloat16* __restrict__ norm_w, float eps,
+            const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int ldr,
+            int out_f32) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem);  // [MT][K]
+    __shared__ float s_red[MT][GEMV_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kv = K / 8;
+
+    // ---- stage x (with optional RMSNorm)
+    float ss[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) ss[m] = 0.f;
+    for (int i = tid; i < kv; i += GEMV_THREADS) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            uint4 v = *(reinterpret_cast<const uint4*>(x + (size_t)m * ldx) + i);
+            reinterpret_cast<uint4*>(sx + (size_t)m * K)[i] = v;
+            if (norm_w != nullptr) {
+                float2 f;
+                f = unpack_bf16(v.x); ss[m] += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(v.y); ss[m] += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(v.z); ss[m] += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(v.w); ss[m] += f.x * f.x + f.y * f.y;
+            }
+        }
+    }
+    if (norm_w != nullptr) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            float v = warp_sum(ss[m]);
+            if (lane == 0) s_red[m][warp] = v;
+        }
+        __syncthreads();
+        float rstd[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < GEMV_THREADS / 32; ++w) t += s_red[m][w];
+            rstd[m] = rsqrtf(t / K + eps);
+        }
+        for (int i = tid; i < kv; i += GEMV_THREADS) {
+            uint4 wv = __ldg(reinterpret_cast<const uint4*>(norm_w) + i);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                uint4 v = reinterpret_cast<uint4*>(sx + (size_t)m * K)[i], o;
+                float2 f, g;
+                f = unpack_bf16(v.x); g = unpack_bf16(wv.x); o.x = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
+                f = unpack_bf16(v.y); g = unpack_bf16(wv.y); o.y = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
+                f = unpack_bf16(v.z); g = unpack_bf16(wv.z); o.z = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
+                f = unpack_bf16(v.w); g = unpack_bf16(wv.w); o.w = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
+                reinterpret_cast<uint4*>(sx + (size_t)m * K)[i] = o;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int n_out = SWIGLU ? N / 2 : N;
+    const int gw = blockIdx.x * (GEMV_THREADS / 32) + warp;
+    const int nw = gridDim.x * (GEMV_THREADS / 32);
+    // two weight rows in flight per warp iteration (SWIGLU: gate row + up row of the same output)
+    for (int o0 = gw * 2; o0 < (SWIGLU ? n_out * 2 : n_out); o0 += nw * 2) {
+        int r0, r1, oc0, oc1;
+        if (SWIGLU) {
+            const int oc = o0 / 2;  // output column
+            oc0 = oc1 = oc;
+            r0 = (oc / 128) * 256 + (oc % 128);  // gate row (interleaved per 256-row block)
+            r1 = r0 + 128;                       // up row
+        } else {
+            oc0 = o0; oc1 = o0 + 1;
+            r0 = o0; r1 = (o0 + 1 < N) ? o0 + 1 : o0;
+        }
+        const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)r0 * ldw);
+        const uint4* w1 = reinterpret_cast<const uint4*>(W + (size_t)r1 * ldw);
+        float a0[MT], a1[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
+#pragma unroll 4
+        for (int i = lane; i < kv; i += 32) {
+            uint4 v0 = ldg_stream(w0 + i), v1 = ldg_stream(w1 + i);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                uint4 xv = reinterpret_cast<const uint4*>(sx + (size_t)m * K)[i];
+                a0[m] += dot8(v0, xv);
+                a1[m] += dot8(v1, xv);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (SWIGLU) {
+                    const float g = bf16r(a0[m]), u = bf16r(a1[m]);
+                    const float y = u * bf16r(silu_f(g));
+                    reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + oc0] = __float2bfloat16_rn(y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int oc = j == 0 ? oc0 : oc1;
+                        if (oc >= N || (j == 1 && oc1 == oc0)) continue;
+                        float y = j == 0 ? a0[m] : a1[m];
+                        if (bias) y += __bfloat162float(bias[oc]);
+                        y = bf16r(y);
+                        if (residual) y = bf16r(y + __bfloat162float(residual[(size_t)m * ldr + oc]));
+                        if (out_f32) reinterpret_cast<float*>(out)[(size_t)m * ldo + oc] = y;
+                        else reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + oc] = __float2bfloat16_rn(y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- decode attention
+constexpr int DA_THREADS = 128;
+constexpr int DA_CHUNK = 256;  // context tokens per CTA
+
+// grid (heads, max_splits). 4 lanes share one token (D/4 elements each); 32 tokens per CTA iteration.
+template <int D>
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                   const __nv_bfloat16* __restrict__ vc, float* __restrict__ ws, const int* __restrict__ ctx_len_dev,
+                   int heads, int kv_heads, int max_ctx, float scale) {
+    constexpr int EPL = D / 4;  // elements per lane
+    constexpr int VPL = EPL / 8;
+    const int ctx = *ctx_len_dev;  // tokens in the cache INCLUDING the one appended this step
+    const int h = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+    const int hk = h / (heads / kv_heads);
+    const int t0 = split * DA_CHUNK;
+    float* wrow = ws + ((size_t)h * nsplit + split) * (D + 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (t0 >= ctx) {
+        if (tid == 0) { wrow[0] = -INFINITY; wrow[1] = 0.f; }
+        return;
+    }
+    const int t1 = min(t0 + DA_CHUNK, ctx);
+    __shared__ float s_sc[DA_CHUNK];
+    __shared__ float s_red[DA_THREADS / 32];
+    __shared__ float s_o[DA_THREADS / 32][D];
+
+    const int sub = lane & 3;         // which quarter of the head dim
+    const int tl = tid >> 2;          // token lane within the 32-token group
+    float qf[EPL];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)h * D + sub * EPL);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            uint4 v = __ldg(qp + i);
+            float2 f;
+            f = unpack_bf16(v.x); qf[i * 8 + 0] = f.x; qf[i * 8 + 1] = f.y;
+            f = unpack_bf16(v.y); qf[i * 8 + 2] = f.x; qf[i * 8 + 3] = f.y;
+            f = unpack_bf16(v.z); qf[i * 8 + 4] = f.x; qf[i * 8 + 5] = f.y;
+            f = unpack_bf16(v.w); qf[i * 8 + 6] = f.x; qf[i * 8 + 7] = f.y;
+        }
+    }
+    const __nv_bfloat16* kbase = kc + (size_t)hk * max_ctx * D;
+    const __nv_bfloat16* vbase = vc + (size_t)hk * max_ctx * D;
+    // ---- pass 1: scores
+    float lmax = -INFINITY;
+    for (int t = t0 + tl; t < t0 + DA_CHUNK; t += DA_THREADS / 4) {
+        float s = 0.f;
+        if (t < t1) {
+            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (size_t)t * D + sub * EPL);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                uint4 v = ldg_stream(kp + i);
+                float2 f;
+                f = unpack_bf16(v.x); s += qf[i * 8 + 0] * f.x + qf[i * 8 + 1] * f.y;
+                f = unpack_bf16(v.y); s += qf[i * 8 + 2] * f.x + qf[i * 8 + 3] * f.y;
+                f = unpack_bf16(v.z); s += qf[i * 8 + 4] * f.x + qf[i * 8 + 5] * f.y;
+                f = unpack_bf16(v.w); s += qf[i * 8 + 6] * f.x + qf[i * 8 + 7] * f.y;
+            }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s = (t < t1) ? s * scale : -INFINITY;
+        if (sub == 0) s_sc[t - t0] = s;
+        lmax = fmaxf(lmax, s);
+    }
+    lmax = warp_max(lmax);
+    if (lane == 0) s_red[warp] = lmax;
+    __syncthreads();
+    float bmax = s_red[0];
+#pragma unroll
+    for (int w = 1; w < DA_THREADS / 32; ++w) bmax = fmaxf(bmax, s_red[w]);
+    // ---- pass 2: p = exp(s - max) (rounded to bf16 like the prefill kernel), o += p * v
+    float o[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) o[i] = 0.f;
+    float lsum = 0.f;
+    for (int t = t0 + tl; t < t1; t += DA_THREADS / 4) {
+        const float p = bf16r(__expf(s_sc[t - t0] - bmax));
+        lsum += p;
+        const uint4* vp = reinterpret_cast<const uint4*>(vbase + (size_t)t * D + sub * EPL);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            uint4 v = ldg_stream(vp + i);
+            float2 f;
+            f = unpack_bf16(v.x); o[i * 8 + 0] += p * f.x; o[i * 8 + 1] += p * f.y;
+            f = unpack_bf16(v.y); o[i * 8 + 2] += p * f.x; o[i * 8 + 3] += p * f.y;
+            f = unpack_bf16(v.z); o[i * 8 + 4] += p * f.x; o[i * 8 + 5] += p * f.y;
+            f = unpack_bf16(v.w); o[i * 8 + 6] += p * f.x; o[i * 8 + 7] += p * f.y;
+        }
+    }
+    // reduce over the 8 token lanes of the warp (lanes with equal `sub`), then over warps
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 4);
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    }
+    if (sub != 0) lsum = 0.f;  // each token's p was added by its 4 lanes; count it once
+    lsum = warp_sum(lsum);
+    __syncthreads();  // s_red reuse
+    if (lane == 0) s_red[warp] = lsum;
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) s_o[warp][lane * EPL + i] = o[i];
+    }
+    __syncthreads();
+    if (tid < D) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < DA_THREADS / 32; ++w) acc += s_o[w][tid];
+        wrow[2 + tid] = acc;
+    }
+    if (tid == 0) {
+        float l = 0.f;
+#pragma unroll
+        for (int w = 0; w < DA_THREADS / 32; ++w) l += s_red[w];
+        wrow[0] = bmax;
+        wrow[1] = l;
+    }
+}
+
+// grid = heads, block = D threads
+__global__ void decode_attn_combine(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int nsplit, int D) {
+    const int h = blockIdx.x, d = threadIdx.x;
+    const float* base = ws + (size_t)h * nsplit * (D + 2);
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, base[(size_t)s * (D + 2)]);
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float* r = base + (size_t)s * (D + 2);
+        if (r[0] == -INFINITY) continue;
+        const float wgt = __expf(r[0] - M);
+        num += wgt * r[2 + d];
+        den += wgt * r[1];
+    }
+    o[(size_t)h * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+}
+
+// ---------------------------------------------------------------- greedy sampling / step state
+// first maximal index (torch.argmax tie order); single CTA.
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const float* __restrict__ logits, int n, long long* __restrict__ out) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = logits[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? s_v[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < (blockDim.x >> 5) ? s_i[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) out[0] = bi;
+    }
+}
+
+// x = embed[cur_token]; also bumps nothing. One CTA.
+__global__ void embed_token_kernel(const __nv_bfloat16* __restrict__ table, const DecodeState* __restrict__ st,
+                                   __nv_bfloat16* __restrict__ x, int dim) {
+    const long long tok = st->cur_token;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tok * dim);
+    for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) reinterpret_cast<uint4*>(x)[i] = src[i];
+}
+
+// RoPE for the single new token at position ctx_len (before increment), append k,v to the cache.
+__global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+                                   __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                                   const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
+                                   const DecodeState* __restrict__ st, int heads, int kv_heads, int D, int max_ctx) {
+    const int half = D / 2;
+    const int total = (heads + 2 * kv_heads) * half;
+    const int pos = st->ctx_len;  // slot == position (single unpadded sequence)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int hh = i / half, j = i % half;
+        const __nv_bfloat16* src = qkv + (size_t)hh * D;
+        const float x1 = __bfloat162float(src[j]), x2 = __bfloat162float(src[j + half]);
+        if (hh < heads + kv_heads) {
+            const float c1 = __bfloat162float(cosb[(size_t)pos * D + j]);
+            const float s1 = __bfloat162float(sinb[(size_t)pos * D + j]);
+            const float c2 = __bfloat162float(cosb[(size_t)pos * D + j + half]);
+            const float s2 = __bfloat162float(sinb[(size_t)pos * D + j + half]);
+            const __nv_bfloat16 y1 = __float2bfloat16_rn(bf16r(x1 * c1) + bf16r(-x2 * s1));
+            const __nv_bfloat16 y2 = __float2bfloat16_rn(bf16r(x2 * c2) + bf16r(x1 * s2));
+            if (hh < heads) {
+                q_out[(size_t)hh * D + j] = y1; q_out[(size_t)hh * D + j + half] = y2;
+            } else {
+                __nv_bfloat16* dst = k_cache + ((size_t)(hh - heads) * max_ctx + pos) * D;
+                dst[j] = y1; dst[j + half] = y2;
+            }
+        } else {
+            __nv_bfloat16* dst = v_cache + ((size_t)(hh - heads - kv_heads) * max_ctx + pos) * D;
+            dst[j] = src[j]; dst[j + half] = src[j + half];
+        }
+    }
+}
+
+// After the per-layer rope kernels of a step: attention must see ctx_len+1 tokens. We keep two counters:
+// ctx_len (tokens already in the cache = position of the token being processed) and attn_len = ctx_len+1.
+__global__ void step_begin_kernel(DecodeState* st) { st->attn_len = st->ctx_len + 1; }
+
+// greedy pick + bookkeeping: tokens_out[step] = argmax (or pad after EOS), cur_token = it, ctx_len++, step++.
+__global__ void __launch_bounds__(1024)
+step_end_kernel(const float* __restrict__ logits, int n, DecodeState* st, long long* __restrict__ tokens_out,
+                float* __restrict__ logits_out, long long eos_id, long long pad_id) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    const int step = st->step;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = logits[i];
+        if (logits_out) logits_out[(size_t)step * n + i] = v;
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = s_v[threadIdx.x];
+        bi = s_i[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) {
+            long long tok = bi;
+            if (st->finished) tok = pad_id;
+            else if (eos_id >= 0 && tok == eos_id) st->finished = 1;
+            if (tokens_out) tokens_out[step] = tok;
+            st->cur_token = tok;
+            st->ctx_len = st->ctx_len + 1;
+            st->step = step + 1;
+        }
+    }
+}
+
+}  // namespace
+
+int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, void* out, int ldo, int M, int N,
+              int K, const __nv_bfloat16* norm_w, float eps, const __nv_bfloat16* bias,
+              const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s) {
+    if (M < 1 || M > GEMV_MAXM || K % 256 != 0 || (act != 0 && act != 3)) return GVL_ERR_ARG;
+    if (act == 3 && N % 256 != 0) return GVL_ERR_ARG;
+    const size_t smem = (size_t)M * K * 2;
+    const int rows = act == 3 ? N / 2 : (N + 1) / 2;  // warp work items
+    int grid = num_sms() * 2;
+    const int need = (rows + GEMV_THREADS / 32 - 1) / (GEMV_THREADS / 32);
+    if (grid > need) grid = need;
+#define GEMV_LAUNCH(MT, SW)                                                                                   \
+    do {                                                                                                      \
+        auto kern = gemv_kernel<MT, SW>;                                                                      \
+        static size_t max_set = 0;                                                                            \
+        if (smem > 48 * 1024 && smem > max_set) {                                                             \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+                return GVL_ERR_CUDA;                                                                          \
+            max_set = smem;                                                                                   \
+        }                                                                                                     \
+        kern<<<grid, GEMV_THREADS, smem, s>>>(x, ldx, W, ldw, out, ldo, N, K, norm_w, eps, bias, residual, ldr, out_f32); \
+    } while (0)
+    if (act == 3) {
+        switch (M) { case 1: GEMV_LAUNCH(1, true); break; case 2: GEMV_LAUNCH(2, true); break;
+                     case 3: GEMV_LAUNCH(3, true); break; default: GEMV_LAUNCH(4, true); break; }
+    } else {
+        switch (M) { case 1: GEMV_LAUNCH(1, false); break; case 2: GEMV_LAUNCH(2, false); break;
+                     case 3: GEMV_LAUNCH(3, false); break; default: GEMV_LAUNCH(4, false); break; }
+    }
+#undef GEMV_LAUNCH
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+size_t decode_attention_workspace(int heads, int head_dim, int max_ctx) {
+    const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;
+    return (size_t)heads * nsplit * (head_dim + 2) * sizeof(float);
+}
+
+int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv_bfloat16* vc, __nv_bfloat16* o,
+                     float* ws, const int* ctx_len_dev, int heads, int kv_heads, int head_dim, int max_ctx,
+                     float scale, cudaStream_t s) {
+    const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;
+    dim3 grid(heads, nsplit);
+    if (head_dim == 64) decode_attn_kernel<64><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    else if (head_dim == 96) decode_attn_kernel<96><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    else if (head_dim == 128) decode_attn_kernel<128><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    else return GVL_ERR_ARG;
+    g_launch_count++;
+    if (cudaGetLastError() != cudaSuccess) return GVL_ERR_CUDA;
+    decode_attn_combine<<<heads, head_dim, 0, s>>>(ws, o, nsplit, head_dim);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s) {
+    argmax_kernel<<<1, 1024, 0, s>>>(logits, n, out);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, cudaStream_t s) {
+    embed_token_kernel<<<1, 256, 0, s>>>(table, st, x, dim);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int rope_decode(const __nv_bfloat16* qkv, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache,
+                const __nv_bfloat16* cosb, const __nv_bfloat16* sinb, const DecodeState* st, int heads, int kv_heads,
+                int D, int max_ctx, cudaStream_t s) {
+    const int total = (heads + 2 * kv_heads) * (D / 2);
+    rope_decode_kernel<<<(total + 255) / 256, 256, 0, s>>>(qkv, q_out, k_cache, v_cache, cosb, sinb, st, heads, kv_heads, D, max_ctx);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int step_begin(DecodeState* st, cudaStream_t s) {
+    step_begin_kernel<<<1, 1, 0, s>>>(st);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int step_end(const float* logits, int n, DecodeState* st, long long* tokens_out, float* logits_out, long long eos_id,
+             long long pad_id, cudaStream_t s) {
+    step_end_kernel<<<1, 1024, 0, s>>>(logits, n, st, tokens_out, logits_out, eos_id, pad_id);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+}  // namespace gvl

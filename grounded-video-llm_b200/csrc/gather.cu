@@ -189,6 +189,27 @@ __global__ void clip_pool3_kernel(const float* __restrict__ hs, __nv_bfloat16* _
     }
 }
 
+// ---- per-segment stream concat (llava_next_video.py:563-564): [spatial a_rows | temporal b_rows | newline 1].
+__global__ void visual_concat_kernel(const __nv_bfloat16* __restrict__ a, int a_rows, const __nv_bfloat16* __restrict__ b,
+                                     int b_rows, const __nv_bfloat16* __restrict__ newline,
+                                     __nv_bfloat16* __restrict__ out, int n_seg, int dim) {
+    const int vec = dim / 8;
+    const int per = a_rows + b_rows + 1;
+    const long long total = (long long)n_seg * per * vec;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = int(i % vec);
+        const long long rg = i / vec;
+        const int r = int(rg % per);
+        const int n = int(rg / per);
+        const uint4* src;
+        if (r < a_rows) src = reinterpret_cast<const uint4*>(a + ((size_t)n * a_rows + r) * dim);
+        else if (r < a_rows + b_rows) src = reinterpret_cast<const uint4*>(b + ((size_t)n * b_rows + (r - a_rows)) * dim);
+        else src = reinterpret_cast<const uint4*>(newline);
+        reinterpret_cast<uint4*>(out)[i] = src[c8];
+    }
+}
+
 // ---- prepare_multimodal_inputs (llava_next_video.py:568-596): embed_tokens(ids[:p]) ++ visual ++ embed_tokens(ids[p+1:])
 // ('text' samples: visual appended last). ids has t_text entries with the -200 sentinel at img_pos.
 __global__ void embed_splice_kernel(const long long* __restrict__ ids, int t_text, int img_pos,
@@ -310,6 +331,14 @@ int iv2_pool(const __nv_bfloat16* x, __nv_bfloat16* out, int n_seg, int frames, 
 int clip_pool3(const float* hs, __nv_bfloat16* out, int n_img, cudaStream_t s) {
     const long long total = (long long)n_img * 64 * 128;
     clip_pool3_kernel<<<grid_for(total, 256), 256, 0, s>>>(hs, out, n_img);
+    GVL_LAUNCH_CHECK();
+}
+
+int visual_concat(const __nv_bfloat16* a, int a_rows, const __nv_bfloat16* b, int b_rows,
+                  const __nv_bfloat16* newline, __nv_bfloat16* out, int n_seg, int dim, cudaStream_t s) {
+    if (dim % 8 != 0) return GVL_ERR_ARG;
+    const long long total = (long long)n_seg * (a_rows + b_rows + 1) * (dim / 8);
+    visual_concat_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, a_rows, b, b_rows, newline, out, n_seg, dim);
     GVL_LAUNCH_CHECK();
 }
 

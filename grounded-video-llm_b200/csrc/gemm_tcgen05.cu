@@ -225,7 +225,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
                             if (col_out + g8 * 8 < n_out_total) {
-                                uint4 r = __ldg(rp + g8);
+                                uint4 r = rp[g8];
                                 float2 f;
                                 f = unpack_bf16(r.x); v[g8 * 8 + 0] += f.x; v[g8 * 8 + 1] += f.y;
                                 f = unpack_bf16(r.y); v[g8 * 8 + 2] += f.x; v[g8 * 8 + 3] += f.y;
@@ -239,7 +239,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
                         for (int g4 = 0; g4 < 8; ++g4) {
                             if (col_out + g4 * 4 < n_out_total) {
-                                float4 r = __ldg(rp + g4);
+                                float4 r = rp[g4];
                                 v[g4 * 4 + 0] += r.x; v[g4 * 4 + 1] += r.y;
                                 v[g4 * 4 + 2] += r.z; v[g4 * 4 + 3] += r.w;
                             }
@@ -373,7 +373,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo
         // Prefer the 128x256 tile; fall back to 128x128 when N pads badly or the grid would be small.
         int waste256 = ((N + 255) / 256) * 256 - N;
         long tiles256 = long((M + BM - 1) / BM) * ((N + 255) / 256);
-        BN = (waste256 >= 128 || tiles256 < num_sms()) ? 128 : 256;
+        BN = (waste256 * 8 > N || tiles256 < num_sms()) ? 128 : 256;
         if (act == ACT_SWIGLU) BN = 256;
     }
     CUtensorMap tmA, tmB;

@@ -49,6 +49,8 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream);
 // rowops.cu
 int layernorm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows,
                           int cols, float eps, cudaStream_t s);
+int layernorm_f32_to_f32(const float* x, const float* w, const float* b, float* y, int rows, int cols, float eps,
+                         cudaStream_t s);
 int rmsnorm_bf16(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, __nv_bfloat16* y,
                  long long ldy, int rows, int cols, float eps, cudaStream_t s);
 int iv2_qk_rmsnorm(__nv_bfloat16* qkv, const __nv_bfloat16* wq, const __nv_bfloat16* wk, int rows,
@@ -64,6 +66,8 @@ int iv2_assemble(const __nv_bfloat16* patch, const __nv_bfloat16* cls, const __n
 int hd_merge_newline(const float* hs, const float* sub_gn, __nv_bfloat16* out, int n_img, cudaStream_t s);
 int iv2_pool(const __nv_bfloat16* x, __nv_bfloat16* out, int n_seg, int frames, int dim, cudaStream_t s);
 int clip_pool3(const float* hs, __nv_bfloat16* out, int n_img, cudaStream_t s);
+int visual_concat(const __nv_bfloat16* a, int a_rows, const __nv_bfloat16* b, int b_rows,
+                  const __nv_bfloat16* newline, __nv_bfloat16* out, int n_seg, int dim, cudaStream_t s);
 int embed_splice(const long long* ids, int t_text, int img_pos, const __nv_bfloat16* table,
                  const __nv_bfloat16* visual, int n_vis, __nv_bfloat16* out, int dim, int vis_last,
                  cudaStream_t s);

@@ -1,0 +1,243 @@
+// Decoder stage entry points: Phi3ForCausalLM / LlamaForCausalLM prefill + greedy decode
+// (modeling_phi3.py:1249-1383 Phi3Model.forward, :1034-1095 Phi3DecoderLayer, :629-775 attention,
+//  :458-464 MLP, :1525-1526 lm_head + .float(); modeling_llama.py:934-1044, 699-760, 417-594, 218-238;
+//  the HF GenerationMixin greedy loop invoked at llava_next_video.py:655-661).
+//
+// The object owns a pre-allocated KV cache [layer][k|v][kv_heads][max_ctx][head_dim] (the reference
+// grows a DynamicCache with torch.cat every step, modeling_phi3.py:721), the activation workspace,
+// and a CUDA graph of one decode step. All step bookkeeping (position, current token, EOS flag)
+// lives in device memory so the graph is replayed without host round trips.
+#include <vector>
+#include "gvl_internal.h"
+#include "decode.h"
+#include "../../include/gvl.h"
+
+using namespace gvl;
+
+struct gvl_lm {
+    gvl_lm_weights w;
+    std::vector<gvl_lm_layer> layers;
+    __nv_bfloat16* kv = nullptr;      // [L][2][KVH][max_ctx][hd]
+    // prefill workspace (grown on demand)
+    __nv_bfloat16 *x = nullptr, *h = nullptr, *qkv = nullptr, *q = nullptr, *attn = nullptr, *mid = nullptr;
+    int ws_tokens = 0;
+    // decode workspace
+    __nv_bfloat16 *dx = nullptr, *dqkv = nullptr, *dq = nullptr, *dattn = nullptr, *dmid = nullptr;
+    float* dlogits = nullptr;
+    float* da_ws = nullptr;
+    DecodeState* st = nullptr;
+    long long* first_tok = nullptr;
+    // decode graph (captured per (tokens_out, logits_out, eos, pad) binding)
+    cudaGraphExec_t graph = nullptr;
+    long long* g_tokens = nullptr;
+    float* g_logits = nullptr;
+    long long g_eos = 0, g_pad = 0;
+    bool use_graph = true;
+
+    size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
+    __nv_bfloat16* kcache(int l) const { return kv + (size_t)l * kv_layer_elems(); }
+    __nv_bfloat16* vcache(int l) const { return kcache(l) + (size_t)w.kv_heads * w.max_ctx * w.head_dim; }
+};
+
+namespace {
+
+#define CK(expr)                       \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != GVL_OK) return _rc; \
+    } while (0)
+#define CU(expr)                                   \
+    do {                                           \
+        if ((expr) != cudaSuccess) return GVL_ERR_CUDA; \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)) == cudaSuccess ? GVL_OK : GVL_ERR_NOMEM;
+}
+
+int ensure_prefill_ws(gvl_lm* lm, int S) {
+    if (S <= lm->ws_tokens) return GVL_OK;
+    const gvl_lm_weights& w = lm->w;
+    cudaFree(lm->x); cudaFree(lm->h); cudaFree(lm->qkv); cudaFree(lm->q); cudaFree(lm->attn); cudaFree(lm->mid);
+    lm->x = lm->h = lm->qkv = lm->q = lm->attn = lm->mid = nullptr;
+    lm->ws_tokens = 0;
+    const size_t qkv_n = (size_t)(w.heads + 2 * w.kv_heads) * w.head_dim;
+    CK(dev_alloc(&lm->x, (size_t)S * w.dim));
+    CK(dev_alloc(&lm->h, (size_t)S * w.dim));
+    CK(dev_alloc(&lm->qkv, (size_t)S * qkv_n));
+    CK(dev_alloc(&lm->q, (size_t)S * w.heads * w.head_dim));
+    CK(dev_alloc(&lm->attn, (size_t)S * w.heads * w.head_dim));
+    CK(dev_alloc(&lm->mid, (size_t)S * w.ffn));
+    lm->ws_tokens = S;
+    return GVL_OK;
+}
+
+// One decode step on `s` (graph-capturable: no host-dependent arguments change between steps).
+int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
+                        cudaStream_t s) {
+    const gvl_lm_weights& w = lm->w;
+    const int D = w.dim, H = w.heads, KVH = w.kv_heads, hd = w.head_dim, F = w.ffn;
+    const int qkv_n = (H + 2 * KVH) * hd;
+    const float scale = 1.0f / sqrtf((float)hd);
+    CK(step_begin(lm->st, s));
+    CK(embed_token((const __nv_bfloat16*)w.embed, lm->st, lm->dx, D, s));
+    for (int l = 0; l < w.n_layers; ++l) {
+        const gvl_lm_layer& L = lm->layers[l];
+        CK(gemv_bf16(lm->dx, D, (const __nv_bfloat16*)L.qkv_w, D, lm->dqkv, qkv_n, 1, qkv_n, D,
+                     (const __nv_bfloat16*)L.in_norm_w, w.rms_eps, nullptr, nullptr, 0, 0, 0, s));
+        CK(rope_decode(lm->dqkv, lm->dq, lm->kcache(l), lm->vcache(l), (const __nv_bfloat16*)w.rope_cos,
+                       (const __nv_bfloat16*)w.rope_sin, lm->st, H, KVH, hd, w.max_ctx, s));
+        CK(decode_attention(lm->dq, lm->kcache(l), lm->vcache(l), lm->dattn, lm->da_ws, &lm->st->attn_len, H, KVH, hd,
+                            w.max_ctx, scale, s));
+        CK(gemv_bf16(lm->dattn, H * hd, (const __nv_bfloat16*)L.o_w, H * hd, lm->dx, D, 1, D, H * hd, nullptr, 0.f,
+                     nullptr, lm->dx, D, 0, 0, s));
+        CK(gemv_bf16(lm->dx, D, (const __nv_bfloat16*)L.gate_up_w, D, lm->dmid, F, 1, 2 * F, D,
+                     (const __nv_bfloat16*)L.post_norm_w, w.rms_eps, nullptr, nullptr, 0, 3, 0, s));
+        CK(gemv_bf16(lm->dmid, F, (const __nv_bfloat16*)L.down_w, F, lm->dx, D, 1, D, F, nullptr, 0.f, nullptr,
+                     lm->dx, D, 0, 0, s));
+    }
+    CK(gemv_bf16(lm->dx, D, (const __nv_bfloat16*)w.lm_head_w, D, lm->dlogits, w.vocab, 1, w.vocab, D,
+                 (const __nv_bfloat16*)w.final_norm_w, w.rms_eps, (const __nv_bfloat16*)w.lm_head_b, nullptr, 0, 0, 1,
+                 s));
+    CK(step_end(lm->dlogits, w.vocab, lm->st, tokens_out, logits_out, eos_id, pad_id, s));
+    return GVL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
+    if (!w || !out || w->n_layers <= 0 || !w->layers) return GVL_ERR_ARG;
+    if (w->dim % 256 != 0 || w->ffn % 256 != 0 || (w->heads * w->head_dim) % 256 != 0) return GVL_ERR_ARG;
+    if (w->head_dim != 64 && w->head_dim != 96 && w->head_dim != 128) return GVL_ERR_ARG;
+    gvl_lm* lm = new gvl_lm();
+    lm->w = *w;
+    lm->layers.assign(w->layers, w->layers + w->n_layers);
+    lm->w.layers = lm->layers.data();
+    const int D = w->dim, qkv_n = (w->heads + 2 * w->kv_heads) * w->head_dim;
+    int rc = GVL_OK;
+    if ((rc = dev_alloc(&lm->kv, (size_t)w->n_layers * lm->kv_layer_elems())) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dx, (size_t)D)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dqkv, (size_t)qkv_n)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dq, (size_t)w->heads * w->head_dim)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dattn, (size_t)w->heads * w->head_dim)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dmid, (size_t)w->ffn)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->dlogits, (size_t)w->vocab)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->da_ws, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx) / sizeof(float))) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->st, 1)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->first_tok, 1)) != GVL_OK) goto fail;
+    cudaMemset(lm->st, 0, sizeof(DecodeState));
+    *out = lm;
+    return GVL_OK;
+fail:
+    gvl_lm_destroy(lm);
+    return rc;
+}
+
+void gvl_lm_destroy(gvl_lm* lm) {
+    if (!lm) return;
+    if (lm->graph) cudaGraphExecDestroy(lm->graph);
+    cudaFree(lm->kv);
+    cudaFree(lm->x); cudaFree(lm->h); cudaFree(lm->qkv); cudaFree(lm->q); cudaFree(lm->attn); cudaFree(lm->mid);
+    cudaFree(lm->dx); cudaFree(lm->dqkv); cudaFree(lm->dq); cudaFree(lm->dattn); cudaFree(lm->dmid);
+    cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
+    delete lm;
+}
+
+int gvl_lm_prefill(gvl_lm* lm, const void* embeds, int S, float* logits_out, void* hidden_out, void* stream) {
+    if (!lm || !embeds || S <= 0 || S > lm->w.max_ctx) return GVL_ERR_ARG;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const gvl_lm_weights& w = lm->w;
+    CK(ensure_prefill_ws(lm, S));
+    const int D = w.dim, H = w.heads, KVH = w.kv_heads, hd = w.head_dim, F = w.ffn;
+    const int qkv_n = (H + 2 * KVH) * hd;
+    const float scale = 1.0f / sqrtf((float)hd);
+    CU(cudaMemcpyAsync(lm->x, embeds, (size_t)S * D * 2, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < w.n_layers; ++l) {
+        const gvl_lm_layer& L = lm->layers[l];
+        // Phi3DecoderLayer.forward (modeling_phi3.py:1034-1095)
+        CK(rmsnorm_bf16(lm->x, D, (const __nv_bfloat16*)L.in_norm_w, lm->h, D, S, D, w.rms_eps, s));
+        CK(gemm_bf16(lm->h, D, L.qkv_w, D, lm->qkv, qkv_n, S, qkv_n, D, nullptr, nullptr, nullptr, 0, GVL_ACT_NONE,
+                     GVL_RES_NONE, 0, 0, s));
+        CK(rope_qkv_cache(lm->qkv, lm->q, lm->kcache(l), lm->vcache(l), (const __nv_bfloat16*)w.rope_cos,
+                          (const __nv_bfloat16*)w.rope_sin, nullptr, S, H, KVH, hd, 0, w.max_ctx, s));
+        AttnArgs a;
+        a.q = lm->q; a.k = lm->kcache(l); a.v = lm->vcache(l); a.o = lm->attn;
+        a.q_bs = 0; a.q_ts = (long long)H * hd; a.q_hs = hd;
+        a.k_bs = a.v_bs = 0; a.k_ts = a.v_ts = hd; a.k_hs = a.v_hs = (long long)w.max_ctx * hd;
+        a.o_bs = 0; a.o_ts = (long long)H * hd; a.o_hs = hd;
+        a.batch = 1; a.heads = H; a.kv_heads = KVH; a.sq = S; a.skv = S; a.head_dim = hd;
+        a.scale = scale; a.causal = 1; a.round_scores = 0;
+        CK(attention_fwd(a, s));
+        CK(gemm_bf16(lm->attn, H * hd, L.o_w, H * hd, lm->x, D, S, D, H * hd, nullptr, nullptr, lm->x, D, GVL_ACT_NONE,
+                     GVL_RES_BF16, 0, 0, s));
+        CK(rmsnorm_bf16(lm->x, D, (const __nv_bfloat16*)L.post_norm_w, lm->h, D, S, D, w.rms_eps, s));
+        CK(gemm_bf16(lm->h, D, L.gate_up_w, D, lm->mid, F, S, 2 * F, D, nullptr, nullptr, nullptr, 0, GVL_ACT_SWIGLU,
+                     GVL_RES_NONE, 0, 0, s));
+        CK(gemm_bf16(lm->mid, F, L.down_w, F, lm->x, D, S, D, F, nullptr, nullptr, lm->x, D, GVL_ACT_NONE, GVL_RES_BF16,
+                     0, 0, s));
+    }
+    if (hidden_out) CU(cudaMemcpyAsync(hidden_out, lm->x, (size_t)S * D * 2, cudaMemcpyDeviceToDevice, s));
+    // final norm + lm_head on the LAST position only (the reference computes all S rows and reads one,
+    // modeling_phi3.py:1525-1526)
+    CK(gemv_bf16(lm->x + (size_t)(S - 1) * D, D, (const __nv_bfloat16*)w.lm_head_w, D, lm->dlogits, w.vocab, 1, w.vocab,
+                 D, (const __nv_bfloat16*)w.final_norm_w, w.rms_eps, (const __nv_bfloat16*)w.lm_head_b, nullptr, 0, 0, 1,
+                 s));
+    if (logits_out) CU(cudaMemcpyAsync(logits_out, lm->dlogits, (size_t)w.vocab * 4, cudaMemcpyDeviceToDevice, s));
+    CK(argmax_f32(lm->dlogits, w.vocab, lm->first_tok, s));
+    DecodeState init;
+    init.ctx_len = S; init.attn_len = S; init.step = 0; init.finished = 0; init.cur_token = 0;
+    CU(cudaMemcpyAsync(lm->st, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(&lm->st->cur_token, lm->first_tok, sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    return GVL_OK;
+}
+
+int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
+                  long long pad_id, void* stream) {
+    if (!lm || n_steps < 0) return GVL_ERR_ARG;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (n_steps == 0) return GVL_OK;
+    // The caller guarantees ctx + n_steps <= max_ctx (checked by the Python mirror, which knows S).
+    // step index restarts at 0 for every decode call
+    int zero = 0;
+    CU(cudaMemcpyAsync(&lm->st->step, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+    if (!lm->use_graph) {
+        for (int i = 0; i < n_steps; ++i) CK(enqueue_decode_step(lm, tokens_out, logits_out, eos_id, pad_id, s));
+        return GVL_OK;
+    }
+    if (lm->graph == nullptr || lm->g_tokens != tokens_out || lm->g_logits != logits_out || lm->g_eos != eos_id ||
+        lm->g_pad != pad_id) {
+        if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
+        // warm-up outside capture so cudaFuncSetAttribute calls are not issued while capturing; the
+        // state mutation is undone by re-copying (ctx_len, cur_token) afterwards.
+        DecodeState saved;
+        CU(cudaMemcpyAsync(&saved, lm->st, sizeof(saved), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        CK(enqueue_decode_step(lm, nullptr, nullptr, -1, 0, s));
+        CU(cudaMemcpyAsync(lm->st, &saved, sizeof(saved), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const long long launches_before = g_launch_count;
+        int rc = enqueue_decode_step(lm, tokens_out, logits_out, eos_id, pad_id, s);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        g_launch_count = launches_before;  // captured launches did not execute
+        if (rc != GVL_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); return rc != GVL_OK ? rc : GVL_ERR_CUDA; }
+        e = cudaGraphInstantiate(&lm->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return GVL_ERR_CUDA;
+        lm->g_tokens = tokens_out; lm->g_logits = logits_out; lm->g_eos = eos_id; lm->g_pad = pad_id;
+    }
+    const long long per_step = 2 + (long long)lm->w.n_layers * 7 + 2;
+    for (int i = 0; i < n_steps; ++i) {
+        CU(cudaGraphLaunch(lm->graph, s));
+        g_launch_count += per_step;
+    }
+    return GVL_OK;
+}
+
+const long long* gvl_lm_first_token(gvl_lm* lm) { return lm ? lm->first_tok : nullptr; }
+
+}  // extern "C"

@@ -24,9 +24,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int ROW_WARPS = 4;
 
+template <bool OUT_F32>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                 __nv_bfloat16* __restrict__ y, int rows, int cols, float eps) {
+                 void* __restrict__ yv, int rows, int cols, float eps) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -45,20 +46,25 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
         q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
     const float rstd = rsqrtf(warp_sum(q) / cols + eps);
-    uint2* yr = reinterpret_cast<uint2*>(y + size_t(row) * cols);
     const float4* w4 = reinterpret_cast<const float4*>(w);
     const float4* b4 = reinterpret_cast<const float4*>(b);
     for (int i = lane; i < nv; i += 32) {
         float4 v = xr[i], ww = __ldg(w4 + i), bb = __ldg(b4 + i);
-        uint2 o;
-        o.x = pack_bf16((v.x - mean) * rstd * ww.x + bb.x, (v.y - mean) * rstd * ww.y + bb.y);
-        o.y = pack_bf16((v.z - mean) * rstd * ww.z + bb.z, (v.w - mean) * rstd * ww.w + bb.w);
-        yr[i] = o;
+        float4 r = make_float4((v.x - mean) * rstd * ww.x + bb.x, (v.y - mean) * rstd * ww.y + bb.y,
+                               (v.z - mean) * rstd * ww.z + bb.z, (v.w - mean) * rstd * ww.w + bb.w);
+        if (OUT_F32) {
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(yv) + size_t(row) * cols)[i] = r;
+        } else {
+            uint2 o;
+            o.x = pack_bf16(r.x, r.y);
+            o.y = pack_bf16(r.z, r.w);
+            reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yv) + size_t(row) * cols)[i] = o;
+        }
     }
 }
 
-__device__ __forceinline__ void rms_row(const __nv_bfloat16* __restrict__ xr, const __nv_bfloat16* __restrict__ w,
-                                        __nv_bfloat16* __restrict__ yr, int cols, float eps, int lane) {
+__device__ __forceinline__ void rms_row(const __nv_bfloat16* xr, const __nv_bfloat16* __restrict__ w,
+                                        __nv_bfloat16* yr, int cols, float eps, int lane) {
     const uint4* x4 = reinterpret_cast<const uint4*>(xr);
     const int nv = cols / 8;
     float ss = 0.f;
@@ -107,7 +113,17 @@ qk_rmsnorm_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restri
 int layernorm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows,
                           int cols, float eps, cudaStream_t s) {
     if (cols % 4 != 0 || rows <= 0) return GVL_ERR_ARG;
-    layernorm_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(x, w, b, y, rows, cols, eps);
+    layernorm_kernel<false><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(x, w, b, y, rows, cols, eps);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+// in-place safe (each warp reads its whole row before the write pass touches it... it re-reads, so
+// in == out is NOT allowed); used for CLIP pre_layrnorm (modeling_clip.py:851) whose output stays fp32.
+int layernorm_f32_to_f32(const float* x, const float* w, const float* b, float* y, int rows, int cols, float eps,
+                         cudaStream_t s) {
+    if (cols % 4 != 0 || rows <= 0 || x == y) return GVL_ERR_ARG;
+    layernorm_kernel<true><<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(x, w, b, y, rows, cols, eps);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
