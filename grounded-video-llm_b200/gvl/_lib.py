@@ -84,6 +84,8 @@ _SIGS = {
     "gvl_clip_pool3": (c_i, [c_vp, c_vp, c_i, c_vp]),
     "gvl_embed_splice": (c_i, [c_vp, c_i, c_i, c_vp, c_vp, c_i, c_vp, c_i, c_i, c_vp]),
     "gvl_rope_qkv_cache": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_vp]),
+    "gvl_visual_concat": (c_i, [c_vp, c_i, c_vp, c_i, c_vp, c_vp, c_i, c_i, c_vp]),
+    "gvl_layernorm_f32_out_f32": (c_i, [c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_f, c_vp]),
     "gvl_gemv_bf16": (c_i, [c_vp, c_i, c_vp, c_i, c_vp, c_i, c_i, c_i, c_i, c_vp, c_f, c_vp, c_vp, c_i, c_i, c_i,
                             c_vp]),
     "gvl_decode_attention": (c_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_i, c_i, c_f, c_vp]),

@@ -1,0 +1,126 @@
+"""Host-side integer / string logic of the path, kept call-compatible with the reference:
+tokenizer_image_token, left-padding, temporal-token <-> seconds arithmetic, frame-index sampling and the RoPE
+tables (built once at load; fp32 trig then cast to bf16 exactly as the reference does per forward).
+Bit-exactness matters here: the temporal-token expressions are evaluated literally in IEEE double, in the
+reference's own operation order.
+"""
+import math
+import re
+
+import numpy as np
+import torch
+
+IMAGE_TOKEN_INDEX = -200
+IGNORE_INDEX = -100
+DEFAULT_IMAGE_TOKEN = "<image>"
+GROUNDING_TOKEN = "<timestamp_grounding>"
+
+
+def tokenizer_image_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX, return_tensors=None, device="cpu"):
+    """llava_next_video.py:409-426."""
+    prompt_chunks = [tokenizer(chunk).input_ids for chunk in prompt.split(DEFAULT_IMAGE_TOKEN)]
+    input_ids = []
+    offset = 0
+    if len(prompt_chunks) > 0 and len(prompt_chunks[0]) > 0 and prompt_chunks[0][0] == tokenizer.bos_token_id:
+        offset = 1
+        input_ids.append(prompt_chunks[0][0])
+    sep = [image_token_index] * (offset + 1)
+    pieces = []
+    for i, chunk in enumerate(prompt_chunks):
+        pieces.append(chunk)
+        if i + 1 < len(prompt_chunks):
+            pieces.append(sep)
+    for x in pieces:
+        input_ids.extend(x[offset:])
+    if return_tensors is not None:
+        if return_tensors == "pt":
+            return torch.tensor(input_ids, dtype=torch.long, device=device)
+        raise ValueError(f"Unsupported tensor type: {return_tensors}")
+    return input_ids
+
+
+def left_pad(id_lists, pad_id, max_txt_len):
+    """generate() pre-amble, llava_next_video.py:622-647 (flip / pad / truncate / flip)."""
+    L = min(max(len(x) for x in id_lists), max_txt_len)
+    ids = torch.full((len(id_lists), L), pad_id, dtype=torch.long)
+    mask = torch.zeros((len(id_lists), L), dtype=torch.long)
+    for r, x in enumerate(id_lists):
+        x = list(x)
+        if len(x) > L:
+            x = x[len(x) - L:]
+        ids[r, L - len(x):] = torch.tensor(x, dtype=torch.long)
+        mask[r, L - len(x):] = 1
+    return ids, mask
+
+
+def parse_time_interval(text, duration, num_temporal_tokens=300, llm="phi3.5"):
+    """inference.py:125-134:  seconds = duration * k / num_temporal_tokens, formatted %.2f."""
+    pattern = r"<(\d+)>"
+
+    def replace_func(match):
+        x = int(match.group(1))
+        m = duration * x / num_temporal_tokens
+        if llm == "phi3.5":
+            return f" {m:.2f} seconds"
+        elif llm == "llama3":
+            return f"{m:.2f} seconds"
+        return None
+
+    return re.sub(pattern, replace_func, text)
+
+
+def seconds_to_token_inference(query, duration, num_temporal_tokens=300):
+    """inference.py:107:  k = int(float(sec) / duration * num_temporal_tokens)."""
+    return re.sub(r"(\d+) seconds", lambda m: f"<{int(float(m.group(1)) / duration * num_temporal_tokens)}>", query)
+
+
+def seconds_to_token_training(time, duration, num_temporal_tokens=300):
+    """datasets/mix_grounded.py:78-91:  k = min(int(num_temporal_tokens * time / duration), num_temporal_tokens)."""
+    return min(int(num_temporal_tokens * time / duration), num_temporal_tokens)
+
+
+def get_frame_indices(num_frames, vlen, sample="middle"):
+    """mm_utils/video_utils.py:13-51 (the 'middle' branch used by inference.py:71-75)."""
+    if sample != "middle":
+        raise NotImplementedError("only sample='middle' is on the inference path")
+    acc_samples = min(num_frames, vlen)
+    intervals = np.linspace(start=0, stop=vlen, num=acc_samples + 1).astype(int)
+    frame_indices = [int((intervals[i] + intervals[i + 1] - 1) // 2) for i in range(acc_samples)]
+    if len(frame_indices) < num_frames:
+        frame_indices = frame_indices + [frame_indices[-1]] * (num_frames - len(frame_indices))
+    return frame_indices
+
+
+def spatial_keyframes(num_frames, num_segs):
+    """inference.py:81-83."""
+    per = int(num_frames // num_segs)
+    return [(i * per) + int(per / 2) for i in range(num_segs)]
+
+
+# --------------------------------------------------------------------------------------- RoPE tables
+def longrope_tables(max_ctx, head_dim, base, short_factor, long_factor, max_pos, orig_max_pos, use_long):
+    """Phi3LongRoPEScaledRotaryEmbedding.forward (modeling_phi3.py:371-409) for positions 0..max_ctx-1 -> bf16."""
+    ext = torch.tensor(long_factor if use_long else short_factor, dtype=torch.float32)
+    shape = torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim
+    inv_freq = 1.0 / (ext * base ** shape)
+    pos = torch.arange(max_ctx, dtype=torch.float32)
+    freqs = pos[:, None] * inv_freq[None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    scale = max_pos / orig_max_pos
+    sf = 1.0 if scale <= 1.0 else math.sqrt(1 + math.log(scale) / math.log(orig_max_pos))
+    return (emb.cos() * sf).to(torch.bfloat16), (emb.sin() * sf).to(torch.bfloat16)
+
+
+def plain_rope_tables(max_ctx, head_dim, base, bf16_matmul_quirk=False):
+    """Phi3RotaryEmbedding (modeling_phi3.py:345-368) / LlamaRotaryEmbedding (modeling_llama.py:94-133).
+    bf16_matmul_quirk reproduces the reference's CUDA-autocast behaviour for Llama: the inv_freq @ position matmul
+    is not excluded from autocast there, so both operands and the product are bf16."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    pos = torch.arange(max_ctx, dtype=torch.float32)
+    if bf16_matmul_quirk:
+        freqs = (pos.to(torch.bfloat16).float()[:, None] * inv_freq.to(torch.bfloat16).float()[None, :]).to(torch.bfloat16)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        return emb.float().cos().to(torch.bfloat16), emb.float().sin().to(torch.bfloat16)
+    freqs = pos[:, None] * inv_freq[None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)

@@ -1,0 +1,456 @@
+"""Host-side mirror of the reference's module API for the inference forward path.
+
+Same class / method names and argument meaning as the reference:
+    CLIPVisionModel.forward(pixel_values, output_hidden_states=True).hidden_states[-2]   modeling_clip.py:904-940
+    PretrainInternVideo2.forward(x, mask, use_image, x_vis_return_idx, x_vis_only)        internvideo2.py:970-1040
+    Phi3_5_Projecter / Video_Projecter .forward                                           llava_next_video.py:26-54
+    CausalLM.forward(inputs_embeds=...) / .generate(inputs_embeds=..., ...)               modeling_phi3.py:1466-1551
+    LLAVA_NEXT_VIDEO.encode_images / prepare_multimodal_inputs / generate                 llava_next_video.py:491-666
+All arithmetic happens in libgvl.so through the C ABI (include/gvl.h); torch provides device memory, streams and
+torch.distributed. There is no CPU path: inputs that are not CUDA tensors are moved to the device first.
+"""
+import ctypes
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib, dist as gdist, hostlogic, ops, weights
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CLIPVisionModel:
+    """Spatial stream. Only hidden_states[-2] is materialised (the one consumer reads, llava_next_video.py:505):
+    the 24th layer and post_layernorm the reference also runs are dead work and are skipped."""
+
+    def __init__(self, state_dict, num_heads=16, num_layers=24, image_size=336, device="cuda"):
+        self.device = torch.device(device)
+        self.num_layers = num_layers
+        self.pk = weights.pack_clip(state_dict, num_heads, num_layers - 1, device=self.device, image=image_size)
+        self.w = self.pk.struct
+        self.dim = self.w.dim
+        self.tokens = self.w.n_patch + 1
+        self._ws = None
+
+    def forward(self, pixel_values, output_attentions=None, output_hidden_states=None, return_dict=None):
+        if pixel_values is None:
+            raise ValueError("You have to specify pixel_values")     # modeling_clip.py:846-847
+        if not output_hidden_states:
+            raise ValueError("gvl CLIPVisionModel serves hidden_states[-2] only; call with output_hidden_states=True")
+        lib = _lib.load()
+        pix = pixel_values.to(self.device, torch.float32).contiguous()
+        n = pix.shape[0]
+        if pix.shape[1:] != (3, self.w.image, self.w.image):
+            raise ValueError("pixel_values must be [N,3,%d,%d]" % (self.w.image, self.w.image))
+        need = lib.gvl_clip_workspace(ctypes.byref(self.w), n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        hs = torch.empty((n, self.tokens, self.dim), dtype=torch.float32, device=self.device)
+        rc = lib.gvl_clip_encode(ctypes.byref(self.w), ctypes.c_void_p(pix.data_ptr()), ctypes.c_void_p(hs.data_ptr()),
+                                 n, ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        _lib.check(rc, "gvl_clip_encode")
+        states = [None] * (self.num_layers + 1)
+        states[-2] = hs
+        return SimpleNamespace(last_hidden_state=None, pooler_output=None, hidden_states=tuple(states), attentions=None)
+
+    __call__ = forward
+
+
+class PretrainInternVideo2:
+    """Temporal stream; serves the x_vis_only=True call the VLM makes (llava_next_video.py:532)."""
+
+    def __init__(self, state_dict, num_heads=16, depth=40, num_frames=8, device="cuda"):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.num_frames = num_frames
+        self.heads = num_heads
+        self.sd = state_dict
+        self._packs = {}
+        self._ws = None
+
+    def _pack(self, n_blocks):
+        if n_blocks not in self._packs:
+            self._packs[n_blocks] = weights.pack_iv2(self.sd, self.heads, n_blocks, self.num_frames, device=self.device)
+        return self._packs[n_blocks]
+
+    def forward(self, x, mask=None, use_image=False, x_vis_return_idx=-1, x_vis_only=False):
+        if mask is not None or use_image or not x_vis_only:
+            raise NotImplementedError("only forward(x, None, False, x_vis_return_idx, x_vis_only=True) is on the path")
+        lib = _lib.load()
+        pk = self._pack(self.depth + x_vis_return_idx + 1)          # blocks 0..depth+idx (internvideo2.py:1028-1030)
+        w = pk.struct
+        pix = x.to(self.device, torch.float32).contiguous()
+        n = pix.shape[0]
+        if pix.shape[1:] != (3, self.num_frames, 224, 224):
+            raise ValueError("x must be [N,3,%d,224,224]" % self.num_frames)
+        need = lib.gvl_iv2_workspace(ctypes.byref(w), n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        out = torch.empty((n, 1 + self.num_frames * 256, w.dim), dtype=torch.bfloat16, device=self.device)
+        rc = lib.gvl_iv2_encode(ctypes.byref(w), ctypes.c_void_p(pix.data_ptr()), ctypes.c_void_p(out.data_ptr()), n,
+                                ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        _lib.check(rc, "gvl_iv2_encode")
+        return out
+
+    __call__ = forward
+
+
+class MLP2Projector:
+    """Linear -> GELU(erf) -> Linear with biases: Phi3_5_Projecter / Video_Projecter / LlavaMultiModalProjector."""
+
+    def __init__(self, w0, b0, w1, b1, device="cuda"):
+        self.w0, self.b0, self.w1, self.b1 = weights.pack_mlp2(w0, b0, w1, b1, device)
+
+    def forward(self, x):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)                      # autocast cast at the first Linear
+        h = ops.gemm(x2.contiguous(), self.w0, bias=self.b0, act=ops.ACT_GELU_ERF)
+        y = ops.gemm(h, self.w1, bias=self.b1)
+        return y.reshape(*shp[:-1], y.shape[-1])
+
+    __call__ = forward
+
+
+class CausalLM:
+    """Phi3ForCausalLM / LlamaForCausalLM replacement for one unpadded sequence at a time."""
+
+    def __init__(self, state_dict, arch, num_heads, num_kv_heads, head_dim, rms_eps, rope, max_ctx=4096, device="cuda"):
+        self.device = torch.device(device)
+        self.arch = arch
+        self.rope = dict(rope)
+        self.max_ctx = max_ctx
+        self.sd = state_dict
+        self.cfg = (num_heads, num_kv_heads, head_dim, rms_eps)
+        self._lms = {}
+        self.vocab = state_dict["lm_head.weight"].shape[0]
+        self.dim = state_dict["model.embed_tokens.weight"].shape[1]
+        self._shared = None
+
+    def _tables(self, use_long):
+        r = self.rope
+        hd = self.cfg[2]
+        if r["type"] == "longrope":
+            return hostlogic.longrope_tables(self.max_ctx, hd, r["base"], r["short_factor"], r["long_factor"],
+                                             r["max_pos"], r["orig_max_pos"], use_long)
+        return hostlogic.plain_rope_tables(self.max_ctx, hd, r["base"], bf16_matmul_quirk=r.get("bf16_quirk", False))
+
+    def _get(self, use_long):
+        """One C-side LM object per RoPE table (short / long factor); the weight buffers are shared."""
+        if use_long not in self._lms:
+            lib = _lib.load()
+            cos, sin = self._tables(use_long)
+            h, kvh, hd, eps = self.cfg
+            if self._shared is None:
+                pk = weights.pack_lm(self.sd, self.arch, h, kvh, hd, eps, self.max_ctx, cos, sin, device=self.device)
+                self._shared = pk
+            else:
+                pk = self._shared
+                cos_d = cos.to(self.device)
+                sin_d = sin.to(self.device)
+                pk.tensors += [cos_d, sin_d]
+                pk.struct.rope_cos = ctypes.c_void_p(cos_d.data_ptr())
+                pk.struct.rope_sin = ctypes.c_void_p(sin_d.data_ptr())
+            handle = ctypes.c_void_p()
+            rc = lib.gvl_lm_create(ctypes.byref(pk.struct), ctypes.byref(handle))
+            _lib.check(rc, "gvl_lm_create")
+            self._lms[use_long] = handle
+        return self._lms[use_long]
+
+    @property
+    def embed_table(self):
+        self._get(False)
+        return self._shared.embed
+
+    def get_input_embeddings(self):
+        table = self.embed_table
+        return lambda ids: table[ids]
+
+    def _use_long(self, total_len):
+        r = self.rope
+        if r["type"] != "longrope":
+            return False
+        return total_len > r["orig_max_pos"]
+
+    def prefill(self, inputs_embeds, want_hidden=False, n_new=0):
+        """inputs_embeds [S,D] bf16. Returns (last-position fp32 logits [V], hidden [S,D] or None)."""
+        lib = _lib.load()
+        emb = inputs_embeds.to(self.device, torch.bfloat16).contiguous()
+        S = emb.shape[0]
+        if S + n_new > self.max_ctx:
+            raise ValueError("sequence of %d tokens (+%d new) exceeds max_ctx=%d" % (S, n_new, self.max_ctx))
+        use_long = self._use_long(S)
+        if self._use_long(S + n_new) != use_long:
+            # modeling_phi3.py:1557-1562 recomputes the whole cache when decoding crosses original_max_position
+            raise NotImplementedError("decode crossing the LongRoPE short/long boundary is not supported")
+        lm = self._get(use_long)
+        logits = torch.empty((self.vocab,), dtype=torch.float32, device=self.device)
+        hidden = torch.empty((S, self.dim), dtype=torch.bfloat16, device=self.device) if want_hidden else None
+        rc = lib.gvl_lm_prefill(lm, ctypes.c_void_p(emb.data_ptr()), S, ctypes.c_void_p(logits.data_ptr()),
+                                ctypes.c_void_p(hidden.data_ptr() if want_hidden else 0), _stream())
+        _lib.check(rc, "gvl_lm_prefill")
+        self._active = (lm, S)
+        return logits, hidden
+
+    def forward(self, inputs_embeds=None, input_ids=None, **unused):
+        """CausalLMOutputWithPast-like: .logits fp32 [1,S,V] for ALL positions (test / parity use; the generate path
+        only computes the last row). Batch size 1."""
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_table[input_ids.to(self.device)]
+        emb = inputs_embeds.reshape(-1, inputs_embeds.shape[-1])
+        _, hidden = self.prefill(emb, want_hidden=True)
+        hn = ops.rmsnorm(hidden, self._final_norm(), self.cfg[3])
+        logits = ops.gemm(hn, self._lm_head_padded()[0], bias=self._lm_head_padded()[1])
+        logits = logits[:, : self.vocab].float()
+        return SimpleNamespace(logits=logits[None], past_key_values=None, hidden_states=hidden)
+
+    __call__ = forward
+
+    def _final_norm(self):
+        if not hasattr(self, "_fn"):
+            self._fn = self.sd["model.norm.weight"].to(self.device, torch.bfloat16).contiguous()
+        return self._fn
+
+    def _lm_head_padded(self):
+        """vocab (32366) is not a multiple of 8 -> pad rows for the GEMM used by the all-position test path."""
+        if not hasattr(self, "_lmh"):
+            V = self.vocab
+            Vp = (V + 7) // 8 * 8
+            w = torch.zeros((Vp, self.dim), dtype=torch.bfloat16, device=self.device)
+            w[:V] = self.sd["lm_head.weight"].to(self.device, torch.bfloat16)
+            b = None
+            if "lm_head.bias" in self.sd:
+                b = torch.zeros((Vp,), dtype=torch.bfloat16, device=self.device)
+                b[:V] = self.sd["lm_head.bias"].to(self.device, torch.bfloat16)
+            self._lmh = (w, b)
+        return self._lmh
+
+    def generate(self, inputs_embeds=None, attention_mask=None, eos_token_id=None, pad_token_id=0, do_sample=False,
+                 num_beams=1, max_new_tokens=16, temperature=None, top_p=None, return_logits=False, **unused):
+        """Greedy generate for a batch of left-padded sequences (each row is compacted with its attention_mask and run
+        as an unpadded sequence: identical to the reference's varlen path because padding carries mask 0 and
+        position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, max_new_tokens]."""
+        if do_sample or num_beams != 1:
+            raise NotImplementedError("gvl implements the greedy parity mode (do_sample=False, num_beams=1)")
+        lib = _lib.load()
+        if inputs_embeds.dim() == 2:
+            inputs_embeds = inputs_embeds[None]
+        B = inputs_embeds.shape[0]
+        outs, logs = [], []
+        for b in range(B):
+            emb = inputs_embeds[b]
+            if attention_mask is not None:
+                emb = emb[attention_mask[b].to(emb.device).bool()]
+            first_logits, _ = self.prefill(emb, n_new=max_new_tokens)
+            lm, S = self._active
+            toks = torch.empty((max_new_tokens,), dtype=torch.int64, device=self.device)
+            lg = torch.empty((max_new_tokens, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            # token 0 is the argmax of the prefill logits; decode steps produce tokens 1..n-1
+            first = ctypes.c_void_p(lib.gvl_lm_first_token(lm))
+            n_steps = max_new_tokens - 1
+            if n_steps > 0:
+                rc = lib.gvl_lm_decode(lm, n_steps, ctypes.c_void_p(toks[1:].data_ptr()),
+                                       ctypes.c_void_p(lg[1:].data_ptr() if return_logits else 0),
+                                       -1 if eos_token_id is None else int(eos_token_id), int(pad_token_id), _stream())
+                _lib.check(rc, "gvl_lm_decode")
+            toks[0:1].copy_(_wrap_device_i64(first, self.device))   # first token: one device int64 owned by the lib
+            if return_logits:
+                lg[0].copy_(first_logits)
+            if eos_token_id is not None:
+                toks = _apply_eos(toks, int(eos_token_id), int(pad_token_id))
+            outs.append(toks)
+            logs.append(lg)
+        out = torch.stack(outs, dim=0)
+        if return_logits:
+            return out, torch.stack(logs, dim=0)
+        return out
+
+    def close(self):
+        lib = _lib.load()
+        for h in self._lms.values():
+            lib.gvl_lm_destroy(h)
+        self._lms = {}
+
+
+def _wrap_device_i64(ptr, device):
+    """View one device int64 owned by the library as a torch tensor (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (ptr.value, False), "version": 2}
+    return torch.as_tensor(h, device=device)
+
+
+def _apply_eos(toks, eos, pad):
+    """HF semantics when the FIRST token (from prefill) is already EOS: everything after is pad."""
+    t = toks.clone()
+    hit = (t == eos).nonzero()
+    if hit.numel() > 0:
+        first = int(hit[0])
+        t[first + 1:] = pad
+    return t
+
+
+class LLAVA_NEXT_VIDEO:
+    """Drop-in for models/llava_next_video.py::LLAVA_NEXT_VIDEO on the inference path (phi3.5 and llama3 variants).
+
+    params: dict with the reference's sub-module state_dicts
+        'vision_tower'            CLIPVisionModel.state_dict()
+        'video_encoder'           PretrainInternVideo2.state_dict()
+        'multi_modal_projector'   {'linear_0.weight', ...} (phi3.5) or {'linear_1.weight', 'linear_2.weight', ...} (llama3)
+        'video_projecter'         {'up_proj.weight', 'up_proj.bias', 'down_proj.weight', 'down_proj.bias'}
+        'language_model'          Phi3ForCausalLM / LlamaForCausalLM state_dict (after reset_embeddings; LoRA merged)
+        'glb_GN', 'sub_GN'        (phi3.5)   or 'image_newline' (llama3)
+    """
+
+    def __init__(self, params, llm="phi3.5", tokenizer=None, num_frames=96, num_segs=12, max_txt_len=2048,
+                 lm_cfg=None, clip_cfg=None, iv2_cfg=None, max_ctx=4096, device="cuda"):
+        self.llm = llm
+        self.device = torch.device(device)
+        self.tokenizer = tokenizer
+        self.num_frames, self.num_segs = num_frames, num_segs
+        self.max_txt_len = max_txt_len
+        clip_cfg = clip_cfg or dict(heads=16, layers=24, image=336)
+        iv2_cfg = iv2_cfg or dict(heads=16, depth=40)
+        self.vision_tower = CLIPVisionModel(params["vision_tower"], clip_cfg["heads"], clip_cfg["layers"],
+                                            clip_cfg.get("image", 336), device)
+        self.video_encoder = PretrainInternVideo2(params["video_encoder"], iv2_cfg["heads"], iv2_cfg["depth"],
+                                                  num_frames // num_segs, device)
+        mm = params["multi_modal_projector"]
+        if llm == "phi3.5":
+            self.multi_modal_projector = MLP2Projector(mm["linear_0.weight"], mm["linear_0.bias"], mm["linear_1.weight"],
+                                                       mm["linear_1.bias"], device)
+            self.sub_GN = params["sub_GN"].to(self.device, torch.float32).reshape(-1).contiguous()
+            self.glb_GN = params["glb_GN"].to(self.device, torch.float32).reshape(1, -1).contiguous()
+        else:
+            self.multi_modal_projector = MLP2Projector(mm["linear_1.weight"], mm["linear_1.bias"], mm["linear_2.weight"],
+                                                       mm["linear_2.bias"], device)
+            self.image_newline = params["image_newline"].to(self.device, torch.bfloat16).reshape(-1).contiguous()
+        vp = params["video_projecter"]
+        self.video_projecter = MLP2Projector(vp["up_proj.weight"], vp["up_proj.bias"], vp["down_proj.weight"],
+                                             vp["down_proj.bias"], device)
+        c = lm_cfg
+        self.language_model = CausalLM(params["language_model"], c["arch"], c["heads"], c["kv_heads"], c["head_dim"],
+                                       c["eps"], c["rope"], max_ctx=max_ctx, device=device)
+        self._newline_tok = None
+
+    # ---------------------------------------------------------------- encode_images (llava_next_video.py:491-566)
+    def _encode_units(self, spatial_units, temporal_units):
+        """spatial_units [U,3,336,336], temporal_units [U,fps,3,224,224] -> [U, tokens_per_seg, D] bf16."""
+        U = spatial_units.shape[0]
+        fps = temporal_units.shape[1]
+        lib = _lib.load()
+        hs = self.vision_tower(spatial_units, output_hidden_states=True).hidden_states[-2]       # fp32 [U,577,1024]
+        if self.llm == "phi3.5":
+            feat = ops.hd_merge_newline(hs, self.sub_GN)                                         # [U,156,4096] bf16
+        else:
+            feat = ops.clip_pool3(hs)                                                             # [U,64,1024] bf16
+        sp = self.multi_modal_projector(feat)                                                     # [U,156|64,D]
+        tpix = temporal_units.permute(0, 2, 1, 3, 4).contiguous()                                 # (b s) c t h w
+        xv = self.video_encoder(tpix, None, False, x_vis_return_idx=-2, x_vis_only=True)          # [U,1+fps*256,1408]
+        pooled = ops.iv2_pool(xv, fps)                                                            # [U,fps*16,1408]
+        tm = self.video_projecter(pooled)                                                         # [U,fps*16,D]
+        if self._newline_tok is None:
+            if self.llm == "phi3.5":
+                self._newline_tok = self.multi_modal_projector(self.glb_GN).reshape(-1).contiguous()   # :560-561
+            else:
+                self._newline_tok = self.image_newline
+        D = sp.shape[-1]
+        out = torch.empty((U, sp.shape[1] + tm.shape[1] + 1, D), dtype=torch.bfloat16, device=self.device)
+        rc = lib.gvl_visual_concat(ctypes.c_void_p(sp.data_ptr()), sp.shape[1], ctypes.c_void_p(tm.data_ptr()),
+                                   tm.shape[1], ctypes.c_void_p(self._newline_tok.data_ptr()),
+                                   ctypes.c_void_p(out.data_ptr()), U, D, _stream())
+        _lib.check(rc, "gvl_visual_concat")
+        return out
+
+    def encode_images(self, samples, unit_chunk=48):
+        spatial = samples["spatial_pixel_values"]
+        temporal = samples["temporal_pixel_values"]
+        B, segs = spatial.shape[:2]
+        frames = temporal.shape[1]
+        if frames % segs != 0:
+            raise ValueError("num_frames must be divisible by num_segs")
+        fps = frames // segs
+        n_units = B * segs
+        sp_u = spatial.reshape(n_units, *spatial.shape[2:])
+        tp_u = temporal.reshape(n_units, fps, *temporal.shape[2:])
+        rank, ws = gdist.world()
+        start, cnt = gdist.partition_units(n_units, ws)[rank]
+        blocks = []
+        for s0 in range(start, start + cnt, unit_chunk):
+            s1 = min(s0 + unit_chunk, start + cnt)
+            blocks.append(self._encode_units(sp_u[s0:s1].to(self.device, non_blocking=True),
+                                             tp_u[s0:s1].to(self.device, non_blocking=True)))
+        if blocks:
+            local = torch.cat(blocks, dim=0) if len(blocks) > 1 else blocks[0]
+        else:
+            tps = (156 if self.llm == "phi3.5" else 64) + 16 * fps + 1
+            local = torch.empty((0, tps, self.language_model.dim), dtype=torch.bfloat16, device=self.device)
+        full = gdist.allgather_units(local, n_units)                # the ONE collective on the path
+        return full.reshape(B, segs * full.shape[1], full.shape[2])
+
+    # ---------------------------------------------------------------- prepare_multimodal_inputs (:568-596)
+    def get_input_embeddings(self):
+        return self.language_model.get_input_embeddings()
+
+    def prepare_multimodal_inputs(self, batch_input_ids, batch_labels, batch_attention_mask, batch_image_features,
+                                  batch_image_ids):
+        table = self.language_model.embed_table
+        embeds, masks = [], []
+        for feats, ids, mask, image_ids in zip(batch_image_features, batch_input_ids, batch_attention_mask, batch_image_ids):
+            where = (ids == hostlogic.IMAGE_TOKEN_INDEX).nonzero()
+            if where.numel() != 1:
+                raise ValueError("each prompt must contain exactly one <image> sentinel")
+            pos = int(where[0])
+            vis_last = image_ids == "text"
+            # padding rows (mask 0) hold pad ids: valid table rows, gathered like any other id
+            ids_dev = ids.to(self.device)
+            embeds.append(ops.embed_splice(ids_dev, pos, table, feats.contiguous(), vis_last=vis_last))
+            m = mask.to(self.device)
+            ones = torch.ones(feats.shape[0], dtype=m.dtype, device=self.device)
+            if vis_last:
+                masks.append(torch.cat([m[:pos], m[pos + 1:], torch.zeros_like(ones)]))
+            else:
+                masks.append(torch.cat([m[:pos], ones, m[pos + 1:]]))
+        return torch.stack(embeds, 0), None, torch.stack(masks, 0)
+
+    def tokenizer_image_token(self, prompt, tokenizer, image_token_index=hostlogic.IMAGE_TOKEN_INDEX, return_tensors=None):
+        return hostlogic.tokenizer_image_token(prompt, tokenizer, image_token_index, return_tensors, device="cpu")
+
+    # ---------------------------------------------------------------- generate (:616-666)
+    @torch.inference_mode()
+    def generate(self, samples, **generate_kwargs):
+        if "input_ids" in samples:                       # tokenizer-free entry used by bench / tests
+            id_lists = [list(map(int, x)) for x in samples["input_ids"]]
+            pad_id = int(samples.get("pad_token_id", 0))
+            eos_id = samples.get("eos_token_id")
+        else:
+            id_lists = [self.tokenizer_image_token(t, self.tokenizer) for t in samples["prompts"]]
+            pad_id, eos_id = self.tokenizer.pad_token_id, self.tokenizer.eos_token_id
+        ids, mask = hostlogic.left_pad(id_lists, pad_id, self.max_txt_len)
+        feats = self.encode_images(samples)
+        video_ids = samples.get("video_ids", ["video"] * len(id_lists))
+        embeds, _, masks = self.prepare_multimodal_inputs(ids, None, mask, feats, video_ids)
+        B = embeds.shape[0]
+        rank, ws = gdist.world()
+        mine = gdist.clips_for_rank(B, rank, ws)
+        gk = dict(generate_kwargs)
+        gk.setdefault("do_sample", False)
+        local = {}
+        for b in mine:
+            local[b] = self.language_model.generate(inputs_embeds=embeds[b:b + 1], attention_mask=masks[b:b + 1],
+                                                    eos_token_id=eos_id, pad_token_id=pad_id, **gk)[0]
+        if ws > 1:
+            gathered = gdist.gather_strings({b: t.cpu() for b, t in local.items()})
+            merged = {}
+            for d in gathered:
+                merged.update(d)
+            local = merged
+        toks = [local[b] for b in range(B)]
+        if self.tokenizer is not None and "input_ids" not in samples:
+            text = self.tokenizer.batch_decode(torch.stack([t.cpu() for t in toks]), skip_special_tokens=True)
+            return [t.strip() for t in text]
+        return toks

@@ -84,6 +84,12 @@ int gvl_hd_merge_newline(const float* hs, const float* sub_gn, void* out_bf16, i
 int gvl_iv2_pool(const void* x, void* out, int n_seg, int frames, int dim, void* stream);
 /* AdaptiveAvgPool3d([segs,8,8]) of the spatial stream, Llama variant (llava_next_video.py:509-517). */
 int gvl_clip_pool3(const float* hs, void* out_bf16, int n_img, void* stream);
+/* per-segment stream concat [spatial a_rows | temporal b_rows | newline 1] (llava_next_video.py:563-564). */
+int gvl_visual_concat(const void* a, int a_rows, const void* b, int b_rows, const void* newline, void* out, int n_seg,
+                      int dim, void* stream);
+/* nn.LayerNorm with fp32 output: CLIP pre_layrnorm (modeling_clip.py:851). x and y must not alias. */
+int gvl_layernorm_f32_out_f32(const float* x, const float* w, const float* b, float* y, int rows, int cols, float eps,
+                              void* stream);
 /* prepare_multimodal_inputs (llava_next_video.py:568-596); ids int64 with the -200 sentinel at img_pos. */
 int gvl_embed_splice(const long long* ids, int t_text, int img_pos, const void* table, const void* visual,
                      int n_vis, void* out, int dim, int vis_last, void* stream);
