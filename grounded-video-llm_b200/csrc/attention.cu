@@ -271,14 +271,20 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
     if (a.head_dim % 8 != 0 || a.head_dim > 128 || a.heads % a.kv_heads != 0) return GVL_ERR_ARG;
     if (a.sq <= 0 || a.skv <= 0) return GVL_ERR_ARG;
     const int hd = (a.head_dim + 15) / 16 * 16;
+    // algorithmic FLOPs: 4*Sq*Skv*D per (batch, head), halved under the causal mask
+    prof_begin(GVL_PROF_ATTN, 4.0 * a.batch * a.heads * (double)a.sq * a.skv * a.head_dim * (a.causal ? 0.5 : 1.0), stream);
+    int rc;
     if (a.causal) {
-        if (hd <= 64) return launch_attn<64, true>(a, stream);
-        if (hd <= 96) return launch_attn<96, true>(a, stream);
-        return launch_attn<128, true>(a, stream);
+        if (hd <= 64) rc = launch_attn<64, true>(a, stream);
+        else if (hd <= 96) rc = launch_attn<96, true>(a, stream);
+        else rc = launch_attn<128, true>(a, stream);
+    } else {
+        if (hd <= 64) rc = launch_attn<64, false>(a, stream);
+        else if (hd <= 96) rc = launch_attn<96, false>(a, stream);
+        else rc = launch_attn<128, false>(a, stream);
     }
-    if (hd <= 64) return launch_attn<64, false>(a, stream);
-    if (hd <= 96) return launch_attn<96, false>(a, stream);
-    return launch_attn<128, false>(a, stream);
+    prof_end(GVL_PROF_ATTN, stream);
+    return rc;
 }
 
 }  // namespace gvl

@@ -431,6 +431,7 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
     if (M < 1 || M > GEMV_MAXM || K % 256 != 0 || (act != 0 && act != 3)) return GVL_ERR_ARG;
     if (act == 3 && N % 256 != 0) return GVL_ERR_ARG;
     const size_t smem = (size_t)M * K * 2;
+    prof_begin(GVL_PROF_GEMV, 2.0 * (double)N * K, s);  // algorithmic bytes: the weight matrix, read once
     const int rows = act == 3 ? N / 2 : (N + 1) / 2;  // warp work items
     int grid = num_sms() * 2;
     const int need = (rows + GEMV_THREADS / 32 - 1) / (GEMV_THREADS / 32);
@@ -454,6 +455,7 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
                      case 3: GEMV_LAUNCH(3, false); break; default: GEMV_LAUNCH(4, false); break; }
     }
 #undef GEMV_LAUNCH
+    prof_end(GVL_PROF_GEMV, s);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }

@@ -390,8 +390,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo
     p.ldo = ldo; p.ldr = ldr;
     p.num_m_tiles = (M + BM - 1) / BM;
     p.num_n_tiles = (N + BN - 1) / BN;
-    if (BN == 256) return dispatch_gemm<256>(tmA, tmB, p, act, res, out_f32, stream);
-    return dispatch_gemm<128>(tmA, tmB, p, act, res, out_f32, stream);
+    prof_begin(GVL_PROF_GEMM, 2.0 * M * (double)N * K, stream);
+    rc = (BN == 256) ? dispatch_gemm<256>(tmA, tmB, p, act, res, out_f32, stream)
+                     : dispatch_gemm<128>(tmA, tmB, p, act, res, out_f32, stream);
+    prof_end(GVL_PROF_GEMM, stream);
+    return rc;
 }
 
 }  // namespace gvl

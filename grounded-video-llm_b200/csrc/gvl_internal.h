@@ -22,6 +22,16 @@ extern long long g_launch_count;  // kernels launched by this library (bench.py:
 
 int num_sms();
 
+// profile.cu -- optional CUDA-event timing per kernel family (off by default)
+#define GVL_PROF_GEMM 0
+#define GVL_PROF_ATTN 1
+#define GVL_PROF_GEMV 2
+#define GVL_PROF_DECODE_ATTN 3
+#define GVL_PROF_KINDS 4
+bool prof_enabled();
+void prof_begin(int kind, double work, cudaStream_t s);
+void prof_end(int kind, cudaStream_t s);
+
 // gemm_tcgen05.cu
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);

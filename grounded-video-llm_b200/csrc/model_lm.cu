@@ -29,8 +29,13 @@ struct gvl_lm {
     long long* first_tok = nullptr;
     // decode graph (captured per (tokens_out, logits_out, eos, pad) binding)
     cudaGraphExec_t graph = nullptr;
-    long long* g_tokens = nullptr;
     float* g_logits = nullptr;
+    long long* tok_buf = nullptr;     // [max_ctx] generated tokens of the current decode call
+    float* logit_buf = nullptr;       // [logit_steps][vocab], only when the caller asks for logits
+    int logit_steps = 0;
+    cudaStream_t cs = nullptr;        // capture / replay stream
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    bool warmed = false;
     long long g_eos = 0, g_pad = 0;
     bool use_graph = true;
 
@@ -128,6 +133,10 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
     if ((rc = dev_alloc(&lm->da_ws, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx) / sizeof(float))) != GVL_OK) goto fail;
     if ((rc = dev_alloc(&lm->st, 1)) != GVL_OK) goto fail;
     if ((rc = dev_alloc(&lm->first_tok, 1)) != GVL_OK) goto fail;
+    if ((rc = dev_alloc(&lm->tok_buf, (size_t)w->max_ctx)) != GVL_OK) goto fail;
+    if (cudaStreamCreateWithFlags(&lm->cs, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&lm->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&lm->ev_out, cudaEventDisableTiming) != cudaSuccess) { rc = GVL_ERR_CUDA; goto fail; }
     cudaMemset(lm->st, 0, sizeof(DecodeState));
     *out = lm;
     return GVL_OK;
@@ -143,6 +152,10 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->x); cudaFree(lm->h); cudaFree(lm->qkv); cudaFree(lm->q); cudaFree(lm->attn); cudaFree(lm->mid);
     cudaFree(lm->dx); cudaFree(lm->dqkv); cudaFree(lm->dq); cudaFree(lm->dattn); cudaFree(lm->dmid);
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
+    cudaFree(lm->tok_buf); cudaFree(lm->logit_buf);
+    if (lm->cs) cudaStreamDestroy(lm->cs);
+    if (lm->ev_in) cudaEventDestroy(lm->ev_in);
+    if (lm->ev_out) cudaEventDestroy(lm->ev_out);
     delete lm;
 }
 
@@ -196,48 +209,74 @@ int gvl_lm_prefill(gvl_lm* lm, const void* embeds, int S, float* logits_out, voi
 
 int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
                   long long pad_id, void* stream) {
-    if (!lm || n_steps < 0) return GVL_ERR_ARG;
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!lm || n_steps < 0 || n_steps > lm->w.max_ctx) return GVL_ERR_ARG;
+    cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
     if (n_steps == 0) return GVL_OK;
     // The caller guarantees ctx + n_steps <= max_ctx (checked by the Python mirror, which knows S).
-    // step index restarts at 0 for every decode call
+    // Steps run on the object's own stream (the caller's may be the legacy default stream, which cannot be
+    // captured), fenced against the caller's stream with events on both sides.
+    cudaStream_t s = lm->cs;
+    CU(cudaEventRecord(lm->ev_in, caller));
+    CU(cudaStreamWaitEvent(s, lm->ev_in, 0));
+    // results land in internal buffers so that the captured graph does not depend on caller pointers
+    const bool want_logits = logits_out != nullptr;
+    if (want_logits && lm->logit_steps < n_steps) {
+        cudaFree(lm->logit_buf);
+        lm->logit_buf = nullptr;
+        CK(dev_alloc(&lm->logit_buf, (size_t)n_steps * lm->w.vocab));
+        lm->logit_steps = n_steps;
+        if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
+    }
+    float* lbuf = want_logits ? lm->logit_buf : nullptr;
     int zero = 0;
     CU(cudaMemcpyAsync(&lm->st->step, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
     if (!lm->use_graph) {
-        for (int i = 0; i < n_steps; ++i) CK(enqueue_decode_step(lm, tokens_out, logits_out, eos_id, pad_id, s));
-        return GVL_OK;
+        for (int i = 0; i < n_steps; ++i) CK(enqueue_decode_step(lm, lm->tok_buf, lbuf, eos_id, pad_id, s));
+    } else {
+        if (lm->graph == nullptr || lm->g_logits != lbuf || lm->g_eos != eos_id || lm->g_pad != pad_id) {
+            if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
+            if (!lm->warmed) {
+                // one eager step outside capture so that cudaFuncSetAttribute is never issued while capturing;
+                // its state mutation is undone by restoring the DecodeState (the KV slot is rewritten later).
+                DecodeState saved;
+                CU(cudaMemcpyAsync(&saved, lm->st, sizeof(saved), cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                CK(enqueue_decode_step(lm, nullptr, nullptr, -1, 0, s));
+                CU(cudaMemcpyAsync(lm->st, &saved, sizeof(saved), cudaMemcpyHostToDevice, s));
+                CU(cudaStreamSynchronize(s));
+                lm->warmed = true;
+            }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const long long launches_before = g_launch_count;
+            int rc = enqueue_decode_step(lm, lm->tok_buf, lbuf, eos_id, pad_id, s);
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            g_launch_count = launches_before;  // captured launches did not execute
+            if (rc != GVL_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); return rc != GVL_OK ? rc : GVL_ERR_CUDA; }
+            e = cudaGraphInstantiate(&lm->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return GVL_ERR_CUDA;
+            lm->g_logits = lbuf; lm->g_eos = eos_id; lm->g_pad = pad_id;
+        }
+        const long long per_step = 2 + (long long)lm->w.n_layers * 7 + 2;
+        for (int i = 0; i < n_steps; ++i) {
+            CU(cudaGraphLaunch(lm->graph, s));
+            g_launch_count += per_step;
+        }
     }
-    if (lm->graph == nullptr || lm->g_tokens != tokens_out || lm->g_logits != logits_out || lm->g_eos != eos_id ||
-        lm->g_pad != pad_id) {
-        if (lm->graph) { cudaGraphExecDestroy(lm->graph); lm->graph = nullptr; }
-        // warm-up outside capture so cudaFuncSetAttribute calls are not issued while capturing; the
-        // state mutation is undone by re-copying (ctx_len, cur_token) afterwards.
-        DecodeState saved;
-        CU(cudaMemcpyAsync(&saved, lm->st, sizeof(saved), cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        CK(enqueue_decode_step(lm, nullptr, nullptr, -1, 0, s));
-        CU(cudaMemcpyAsync(lm->st, &saved, sizeof(saved), cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));
-        cudaGraph_t g = nullptr;
-        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const long long launches_before = g_launch_count;
-        int rc = enqueue_decode_step(lm, tokens_out, logits_out, eos_id, pad_id, s);
-        cudaError_t e = cudaStreamEndCapture(s, &g);
-        g_launch_count = launches_before;  // captured launches did not execute
-        if (rc != GVL_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); return rc != GVL_OK ? rc : GVL_ERR_CUDA; }
-        e = cudaGraphInstantiate(&lm->graph, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return GVL_ERR_CUDA;
-        lm->g_tokens = tokens_out; lm->g_logits = logits_out; lm->g_eos = eos_id; lm->g_pad = pad_id;
-    }
-    const long long per_step = 2 + (long long)lm->w.n_layers * 7 + 2;
-    for (int i = 0; i < n_steps; ++i) {
-        CU(cudaGraphLaunch(lm->graph, s));
-        g_launch_count += per_step;
-    }
+    if (tokens_out) CU(cudaMemcpyAsync(tokens_out, lm->tok_buf, (size_t)n_steps * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    if (want_logits) CU(cudaMemcpyAsync(logits_out, lbuf, (size_t)n_steps * lm->w.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU(cudaEventRecord(lm->ev_out, s));
+    CU(cudaStreamWaitEvent(caller, lm->ev_out, 0));
     return GVL_OK;
 }
 
 const long long* gvl_lm_first_token(gvl_lm* lm) { return lm ? lm->first_tok : nullptr; }
+
+int gvl_lm_set_graph(gvl_lm* lm, int on) {
+    if (!lm) return GVL_ERR_ARG;
+    lm->use_graph = on != 0;
+    return GVL_OK;
+}
 
 }  // extern "C"

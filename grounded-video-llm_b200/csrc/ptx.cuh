@@ -214,9 +214,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // a bf16 tensor: mul -> sigmoid -> mul).
 __device__ __forceinline__ float quick_gelu_bf16(float x) {
     float t = bf16r(1.702f * x);
-    float s = bf16r(1.0f / (1.0f + __expf(-t)));
+    float s = bf16r(__fdividef(1.0f, 1.0f + __expf(-t)));  // approximate division: no data-dependent slow path
     return bf16r(x * s);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace gvl

@@ -100,6 +100,10 @@ _SIGS = {
     "gvl_lm_prefill": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "gvl_lm_decode": (c_i, [c_vp, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_first_token": (c_vp, [c_vp]),
+    "gvl_lm_set_graph": (c_i, [c_vp, c_i]),
+    "gvl_profile_enable": (c_i, [c_i]),
+    "gvl_profile_collect": (c_i, [c_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(c_ll)]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

@@ -202,6 +202,15 @@ int gvl_lm_prefill(gvl_lm* lm, const void* embeds, int S, float* logits_out, voi
  * after EOS the remaining slots are filled with pad_id (HF generate semantics).                    */
 int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
                   long long pad_id, void* stream);
+/* replay decode steps from a captured CUDA graph (default 1) or launch them one by one (0; needed while profiling) */
+int gvl_lm_set_graph(gvl_lm* lm, int on);
+
+/* ------------------------------------------------------------------ measurement hooks (bench.py roofline)
+ * When enabled, every launch of a kernel family is bracketed by CUDA events on its launching stream.
+ * kind: 0 tcgen05 GEMM (work = FLOPs), 1 prefill attention (FLOPs), 2 decode GEMV (weight bytes).        */
+int gvl_profile_enable(int on);
+int gvl_profile_collect(int kind, double* total_ms, double* total_work, long long* launches);
+
 /* first generated token (argmax of the prefill logits), device int64 */
 const long long* gvl_lm_first_token(gvl_lm* lm);
 

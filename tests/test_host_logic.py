@@ -1,0 +1,100 @@
+"""Product-side host logic (gvl/hostlogic.py, gvl/dist.py, gvl/weights.py) -- no GPU, no oracle in the product path;
+the oracle / goldens are only the checker here."""
+import json
+import os
+
+import pytest
+import torch
+
+from gvl import dist as gdist
+from gvl import hostlogic as H
+from gvl import weights
+from oracle import gvl_oracle as O
+
+
+class Tok:
+    bos_token_id = 1
+
+    def __init__(self, bos):
+        self.bos = bos
+
+    def __call__(self, s):
+        ids = ([1] if self.bos else []) + [3 + (ord(c) % 50) for c in s]
+        return type("E", (), {"input_ids": ids})()
+
+
+def test_golden_host_logic(gold_dir):
+    g = json.load(open(os.path.join(gold_dir, "host_logic.json")))
+    for e in g["parse"]:
+        assert H.parse_time_interval(e["text"], e["duration"], 300, e["llm"]) == e["result"]
+    for e in g["frame_indices"]:
+        assert H.get_frame_indices(e["n"], e["vlen"]) == e["result"]
+    for e in g["referring"]:
+        assert H.seconds_to_token_inference(e["query"], e["duration"]) == e["result"]
+    for e in g["training_quant"]:
+        assert H.seconds_to_token_training(e["t"], e["duration"]) == e["result"]
+    for e in g["tokenize"]:
+        assert H.tokenizer_image_token(e["prompt"], Tok(e["bos"])) == e["result"]
+    dur = g["duration"]
+    for k, v in g["readme_kat"].items():
+        assert H.parse_time_interval(k, dur) == " %s seconds" % v
+    assert H.spatial_keyframes(96, 12) == [4 + 8 * i for i in range(12)]
+
+
+def test_temporal_token_roundtrip_all_tokens():
+    # decode(k) then re-encode never drifts by more than one token, and k=0 / k=300 are fixed points
+    dur = 142.04187520854188
+    for k in range(301):
+        txt = H.parse_time_interval("<%d>" % k, dur)
+        sec = float(txt.split()[0])
+        back = H.seconds_to_token_training(sec, dur)
+        assert abs(back - k) <= 1
+    assert H.seconds_to_token_training(dur * 2, dur) == 300
+
+
+def test_left_pad_matches_oracle_and_truncates_tail():
+    lists = [[1, 5, -200, 7], [1, 2, 3, 4, 5, 6, -200, 8, 9], [4]]
+    ids, mask = H.left_pad(lists, 0, 2048)
+    oi, om = O.left_pad_batch(lists, 0, 2048)
+    assert torch.equal(ids, oi) and torch.equal(mask, om)
+    ids, mask = H.left_pad(lists, 0, 5)
+    oi, om = O.left_pad_batch(lists, 0, 5)
+    assert torch.equal(ids, oi) and torch.equal(mask, om)
+    assert ids[1].tolist() == [5, 6, -200, 8, 9]
+    with pytest.raises(ValueError):
+        H.tokenizer_image_token("x", Tok(True), return_tensors="np")
+
+
+def test_rope_tables_match_oracle():
+    r = O.phi35_rope_cfg(96)
+    for use_long in (False, True):
+        cos, sin = H.longrope_tables(300, 96, r["base"], r["short_factor"], r["long_factor"], r["max_pos"], r["orig_max_pos"], use_long)
+        oc, osn = O.phi3_rope_tables(torch.arange(300), 96, r["base"], r["short_factor"], r["long_factor"], r["max_pos"],
+                                     r["orig_max_pos"], seq_len=5000 if use_long else 300)
+        assert torch.equal(cos.float(), O.bf(oc)) and torch.equal(sin.float(), O.bf(osn))
+    cos, sin = H.plain_rope_tables(3000, 128, 500000.0, bf16_matmul_quirk=True)
+    oc, osn = O.plain_rope_tables(torch.arange(3000), 128, 500000.0, bf16_matmul_quirk=True)
+    assert torch.equal(cos.float(), oc) and torch.equal(sin.float(), osn)
+
+
+def test_partition_units():
+    for n in (12, 384, 5, 1):
+        for ws in (1, 2, 4, 8):
+            parts = gdist.partition_units(n, ws)
+            assert sum(c for _, c in parts) == n
+            assert [s for s, _ in parts] == [sum(c for _, c in parts[:i]) for i in range(ws)]
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    assert [c for _, c in gdist.partition_units(12, 8)] == [2, 2, 2, 2, 1, 1, 1, 1]
+    assert gdist.clips_for_rank(32, 3, 8) == [3, 11, 19, 27]
+
+
+def test_gate_up_interleave_and_clip_pack_cpu():
+    g = torch.arange(256 * 2).float().reshape(256, 2)
+    u = -torch.arange(256 * 2).float().reshape(256, 2)
+    w = weights.interleave_gate_up(g, u)
+    assert torch.equal(w[:128], g[:128]) and torch.equal(w[128:256], u[:128]) and torch.equal(w[256:384], g[128:])
+    P = O.make_clip_params(dim=64, heads=4, ffn=128, layers=2, image=56, seed=1)
+    pk = weights.pack_clip(P, 4, 1, device="cpu", image=56)
+    assert pk.struct.kpad == 640 and pk.struct.n_patch == 16 and pk.struct.n_layers == 1
+    with pytest.raises(ValueError):
+        weights.pack_clip(O.make_clip_params(dim=96, heads=4, ffn=128, layers=1, image=56), 4, 1, device="cpu", image=56)
