@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- videos/sec (prefill + decode) of the Grounded-VideoLLM forward path, Phi-3.5-3.8B, 96-frame clips.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+
+One "step" = one pass of the whole hot path over one batch of synthetic clips (BASELINE.json configs[1] at N=1:
+1 clip = 12 CLIP key-frames 336^2 + 96 frames 224^2 -> 3420 visual tokens -> 3483-token prefill -> 16 greedy tokens).
+At N>1 every rank owns `--clips-per-gpu` clips (weak scaling): (clip, segment) units are block-partitioned over the
+ranks, projected visual tokens are exchanged with one NCCL all-gather, the decoder runs clip-sharded.
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "grounded-video-llm_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "videos/sec (prefill+decode) Phi3.5-3.8B 96-frame"
+UNIT = "videos/s"
+DECODE_TOKENS = 16
+T_TEXT = 64                      # 64 ids incl. the <image> sentinel -> S = 3420 + 63
+S_PREFILL = 3420 + T_TEXT - 1
+# algorithmic work per video (identical counting rules)
+FLOPS_CLIP, FLOPS_IV2, FLOPS_PROJ = 4.39e12, 59.50e12, 0.13e12
+FLOPS_LM = 32 * (S_PREFILL * 226.5e6 + 6144.0 * S_PREFILL ** 2) + 2 * 3072 * 32366
+FLOPS_PREFILL = FLOPS_CLIP + FLOPS_IV2 + FLOPS_PROJ + FLOPS_LM
+DECODE_BYTES_WEIGHTS = 7.447e9
+KV_BYTES_PER_CTX_TOKEN = 393216.0
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (reference) arm
+def cpu_reference_sample(threads=None):
+    """The reference's algorithm on the host cores (oracle port, fp32 -- the reference's own CPU mode, BASELINE config 1),
+    timed on a BOUNDED sample of the 96-frame workload and scaled by the layer / unit counts it skips:
+      1 CLIP image x 23 layers (of 12 images), 1 InternVideo2 segment x 2 blocks (of 12 x 39),
+      1 decoder layer prefill at S=3483 (of 32), 1 decoder-layer decode step against a 3483-token cache (of 32 x 16),
+      1 lm_head row. Returns (videos_per_s, seconds_per_video, detail dict)."""
+    import torch
+    from oracle import gvl_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t = {}
+    with torch.inference_mode():
+        P = O.make_clip_params(seed=1)
+        pix = torch.randn(1, 3, 336, 336)
+        t0 = time.perf_counter()
+        O.clip_hidden_states(pix, P, 16, 24, mode="fp32", upto=23)
+        t["clip_image_23_layers"] = time.perf_counter() - t0
+        del P
+        nb = 2
+        P = O.make_iv2_params(depth=nb + 1, seed=3)
+        pix = torch.randn(1, 3, 8, 224, 224)
+        t0 = time.perf_counter()
+        O.iv2_forward(pix, P, 16, nb + 1, mode="fp32", x_vis_return_idx=-2)     # runs blocks 0..nb-1
+        t["iv2_segment_%d_blocks" % nb] = time.perf_counter() - t0
+        del P
+        P = O.make_lm_params(arch="phi3", layers=1, vocab=32366, seed=7)
+        cfg = dict(arch="phi3", layers=1, heads=32, kv_heads=32, head_dim=96, eps=1e-5, rope=O.phi35_rope_cfg(96))
+        emb = torch.randn(S_PREFILL, 3072) * 0.05
+        t0 = time.perf_counter()
+        _, hidden = O.lm_forward(emb[:, :], dict(P, **{"lm_head.weight": P["lm_head.weight"][:8], "lm_head.bias": P["lm_head.bias"][:8]}),
+                                 cfg, mode="fp32", return_hidden=True)
+        t["lm_prefill_1_layer"] = time.perf_counter() - t0
+        # one KV-cached decode step of one layer (the reference decodes with a cache, modeling_phi3.py:721)
+        x = torch.randn(1, 3072) * 0.05
+        kc, vc = torch.randn(32, S_PREFILL, 96), torch.randn(32, S_PREFILL, 96)
+        pre = "model.layers.0."
+        t0 = time.perf_counter()
+        h = O.rmsnorm(x, P[pre + "input_layernorm.weight"], 1e-5, "fp32")
+        qkv = O.linear(h, P[pre + "self_attn.qkv_proj.weight"], None, "fp32")
+        q = qkv[:, :3072].reshape(1, 32, 96).transpose(0, 1)
+        o = O.attention_core(q[None], kc[None], vc[None], 96 ** -0.5, True, "fp32")[0].transpose(0, 1).reshape(1, 3072)
+        x = x + O.linear(o, P[pre + "self_attn.o_proj.weight"], None, "fp32")
+        h = O.rmsnorm(x, P[pre + "post_attention_layernorm.weight"], 1e-5, "fp32")
+        gate, up = O.linear(h, P[pre + "mlp.gate_up_proj.weight"], None, "fp32").chunk(2, -1)
+        x = x + O.linear(up * torch.nn.functional.silu(gate), P[pre + "mlp.down_proj.weight"], None, "fp32")
+        t["lm_decode_step_1_layer"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.linear(O.rmsnorm(x, P["model.norm.weight"], 1e-5, "fp32"), P["lm_head.weight"], P["lm_head.bias"], "fp32")
+        t["lm_head_1_row"] = time.perf_counter() - t0
+    sec = (12 * t["clip_image_23_layers"] + 12 * 39 / nb * t["iv2_segment_%d_blocks" % nb] + 32 * t["lm_prefill_1_layer"]
+           + t["lm_head_1_row"] + (DECODE_TOKENS - 1) * (32 * t["lm_decode_step_1_layer"] + t["lm_head_1_row"]))
+    return 1.0 / sec, sec, t
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, sec, detail = cpu_reference_sample(cores)
+        if i >= args.warmup:
+            vals.append((v, sec, detail))
+    v = sum(x[0] for x in vals) / len(vals)
+    sec = sum(x[1] for x in vals) / len(vals)
+    sample = "1 CLIP image x23 layers + 1 IV2 segment x2 blocks + 1 decoder layer prefill S=%d + 1 decoder-layer decode step + " \
+             "1 lm_head row, fp32, scaled to 12 images / 12x39 blocks / 32 layers / %d tokens (extrapolated)" % (S_PREFILL, DECODE_TOKENS)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "Phi-3.5-3.8B grounding inference, 1 clip = 96 frames (12x336^2 + 96x224^2), prefill S=%d + %d greedy tokens"
+                                  % (S_PREFILL, DECODE_TOKENS), "where": "host CPU, oracle port of the reference (torch fp32)"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "detail_s": vals[-1][2]}
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_gvl_arm(args):
+    import torch
+    import torch.distributed as dist
+    from gvl import _lib, model, ops, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gvl hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    lib = _lib.load()
+    B = world * args.clips_per_gpu
+    params, lm_cfg, clip_cfg, iv2_cfg = synth.make_params("phi3.5", device=dev, seed=0)
+    m = model.LLAVA_NEXT_VIDEO(params, llm="phi3.5", lm_cfg=lm_cfg, clip_cfg=clip_cfg, iv2_cfg=iv2_cfg, max_ctx=4096, device=dev)
+    del params
+    torch.cuda.empty_cache()
+    host = synth.make_clip_inputs(B, pin=True)                       # pinned host buffers (e2e path)
+    resident = dict(host)
+    resident["spatial_pixel_values"] = host["spatial_pixel_values"].to(dev)
+    resident["temporal_pixel_values"] = host["temporal_pixel_values"].to(dev)
+    h2d = host["spatial_pixel_values"].numel() * 4 + host["temporal_pixel_values"].numel() * 4 + B * T_TEXT * 8
+    d2h = B * DECODE_TOKENS * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(samples, to_host):
+        toks = m.generate(samples, max_new_tokens=DECODE_TOKENS)
+        if to_host:
+            return [t.cpu() for t in toks]                             # device -> host read of the step's result
+        return toks
+
+    def timed(samples, to_host, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            a.record()
+            one_step(samples, to_host)
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(resident, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    total_ms = timed(resident, False, args.steps)
+    launches = ops.launch_count() - l0
+    for _ in range(2):
+        one_step(host, True)
+    e2e_ms = timed(host, True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline pass: per-kernel-family CUDA events on the launching stream, one extra step, graph replay off
+    import ctypes
+    roof, extra = None, {}
+    for lmh in m.language_model._lms.values():
+        lib.gvl_lm_set_graph(lmh, 0)
+    lib.gvl_profile_enable(1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier()
+    ev[0].record()
+    feats = m.encode_images(resident)
+    ev[1].record()
+    from gvl import hostlogic
+    ids, mask = hostlogic.left_pad(resident["input_ids"], 0, 2048)
+    mine = [b for b in range(B) if b % world == rank]
+    emb, _, masks = m.prepare_multimodal_inputs(ids[mine], None, mask[mine], feats[mine], ["v"] * len(mine))
+    for i in range(len(mine)):
+        m.language_model.prefill(emb[i], n_new=DECODE_TOKENS)
+    ev[2].record()
+    m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
+    ev[3].record()
+    torch.cuda.synchronize()
+    lib.gvl_profile_enable(0)
+    for lmh in m.language_model._lms.values():
+        lib.gvl_lm_set_graph(lmh, 1)
+    fam = {}
+    for kind, name in ((0, "gemm"), (1, "attn"), (2, "gemv")):
+        ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.gvl_profile_collect(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n))
+        fam[name] = (ms.value, work.value, n.value)
+    pk = _peaks()
+    if rank == 0:
+        g_ms, g_fl, g_n = fam["gemm"]
+        a_ms, a_fl, a_n = fam["attn"]
+        v_ms, v_by, v_n = fam["gemv"]
+        ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"kernel": "gvl::gemm_bf16_tcgen05_kernel (all epilogue variants)", "bound": "tensor", "achieved": ach,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                "share_of_step_ms": g_ms}
+        enc_ms, pre_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        per_rank_clips = len(mine)
+        prefill_s = (enc_ms + pre_ms) * 1e-3
+        units_here = 12 * B / world
+        prefill_flops = units_here * (FLOPS_CLIP + FLOPS_IV2 + FLOPS_PROJ) / 12 + per_rank_clips * FLOPS_LM
+        extra = {
+            "stage_ms_profiled": {"encode_images": enc_ms, "splice+prefill": pre_ms, "prefill+%d_decode" % DECODE_TOKENS: dec_ms},
+            "prefill_tflops_achieved": prefill_flops / prefill_s / 1e12,
+            "prefill_frac_of_tensor_peak": prefill_flops / prefill_s / 1e12 / pk["tf_sustained"],
+            "attention": {"ms": a_ms, "tflops": a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None, "launches": a_n,
+                          "kernel": "gvl::attn_fwd_kernel"},
+            "decode_gemv": {"ms": v_ms, "gbs": v_by / (v_ms * 1e-3) / 1e9 if v_ms > 0 else None, "launches": v_n,
+                            "frac_of_hbm_peak": (v_by / (v_ms * 1e-3) / 1e9 / pk["hbm"]) if v_ms > 0 else None,
+                            "kernel": "gvl::gemv_kernel"},
+            "peaks": pk,
+        }
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, detail = cpu_reference_sample()
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "1 CLIP image x23 layers + 1 IV2 segment x2 blocks + 1 decoder layer prefill + 1 decoder-layer decode step "
+                         "+ 1 lm_head row (fp32 oracle port), scaled to the full clip; %.1f s/video extrapolated" % sec,
+               "detail_s": detail}
+    if rank == 0:
+        value = B * args.steps / (total_ms * 1e-3)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "BASELINE configs[1] x %d clip(s)/GPU: Phi-3.5-3.8B, 96 frames (12 key-frames 336^2 + 96 frames 224^2), "
+                                      "3420 visual tokens, prefill S=%d, %d greedy decode tokens, random-init weights" %
+                                      (args.clips_per_gpu, S_PREFILL, DECODE_TOKENS),
+                          "global_batch": B, "parallelism": "units block-partitioned over %d rank(s); one all-gather of visual tokens; "
+                                                             "decoder clip-sharded" % world,
+                          "l2": "no explicit flush: each step streams 10.9 GB of weights + >1 GB of activations (>> 126 MB L2)",
+                          "timing": "CUDA events per step on the launching stream, barrier+synchronize on both sides, max over ranks"},
+               "clocks": clocks,
+               "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_ms / args.steps, "api": "gvl.model.LLAVA_NEXT_VIDEO.generate(samples) with pinned host tensors"},
+               "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gvl", choices=["gvl", "reference"])
+    ap.add_argument("--clips-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gvl_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,310 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI mirror (gvl.ops / gvl.model), against
+the oracle (oracle/gvl_oracle.py, bf16 mode = the reference's CUDA autocast rounding points) on the same seeded
+inputs. Integer / index work must be bit-exact; floating point tolerances are written next to each assert.
+
+Tolerance rationale: one bf16 ulp is 2^-8 relative; an output of magnitude A that went through the same rounding
+points can differ by ~1 ulp(A) per independent rounding because fp32 accumulation ORDER differs (tensor-core tile
+order vs torch). north_star: logits within 1e-2 max-abs of the reference bf16 forward.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gvl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gvl():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gvl import model, ops
+    return type("G", (), {"ops": ops, "model": model})
+
+
+def _cmp(a, b, atol, rtol=0.0):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    lim = atol + rtol * b.abs()
+    assert bool((err <= lim).all()), "max err %.4g (limit %.4g), ref absmax %.4g" % (err.max(), lim.min(), b.abs().max())
+
+
+# ------------------------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("M,N,K,act,bias,gamma,res,out_f32", [
+    (256, 256, 128, 0, False, False, None, False),
+    (577 * 2, 1024, 1024, 0, True, False, None, False),       # ragged M
+    (2049, 6144, 1408, 1, True, False, None, False),           # IV2 fc1 + GELU(erf)
+    (2049, 1408, 6144, 0, True, True, "bf16", False),         # IV2 fc2 + LayerScale + residual
+    (2049, 4224, 1408, 0, False, False, None, False),          # IV2 qkv (N = 16.5 x 256)
+    (577, 4096, 1024, 2, True, False, None, False),            # CLIP fc1 + quick-GELU
+    (577 * 3, 1024, 4096, 0, True, False, "f32", True),       # CLIP fc2 + fp32 residual stream
+    (700, 16384, 3072, 3, False, False, None, False),          # Phi gate_up + SwiGLU
+    (700, 3072, 8192, 0, False, False, "bf16", False),        # Phi down + residual
+    (2048, 1408, 640, 0, True, False, None, False),            # patch embed (K padded 588 -> 640)
+    (1, 3072, 4096, 1, True, False, None, False),              # glb_GN projector row (M = 1)
+])
+def test_gemm_epilogues_vs_oracle_rounding(gvl, M, N, K, act, bias, gamma, res, out_f32):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = O.bf(torch.randn(M, K, generator=g) * 0.5)
+    w = O.bf(torch.randn(N, K, generator=g) * 0.05)
+    b = O.bf(torch.randn(N, generator=g) * 0.1) if bias else None
+    n_out = N // 2 if act == 3 else N
+    gm = (torch.rand(n_out, generator=g) + 0.5) if gamma else None
+    r = None
+    if res == "bf16":
+        r = O.bf(torch.randn(M, n_out, generator=g))
+    elif res == "f32":
+        r = torch.randn(M, n_out, generator=g)
+    ops = gvl.ops
+    dev = lambda t, dt: None if t is None else t.to("cuda", dt)
+    if act == 3:
+        # interleave gate/up rows the way gvl.weights does; oracle works on the un-interleaved halves
+        from gvl import weights
+        wi = weights.interleave_gate_up(w[: N // 2], w[N // 2:])
+    else:
+        wi = w
+    out = ops.gemm(dev(a, torch.bfloat16), dev(wi, torch.bfloat16), bias=dev(b, torch.bfloat16), act=act,
+                   gamma=dev(gm, torch.float32), residual=dev(r, torch.float32 if res == "f32" else torch.bfloat16),
+                   out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+    y = O.linear(a, w, b, "bf16")
+    if act == 1:
+        y = O.gelu_erf(y, "bf16")
+    elif act == 2:
+        y = O.quick_gelu(y, "bf16")
+    elif act == 3:
+        gate, up = y.chunk(2, dim=-1)
+        y = O.bf(up * O.bf(torch.nn.functional.silu(gate)))
+    if gm is not None:
+        y = O.bf(y * gm)
+    if r is not None:
+        y = y + r
+    if not out_f32:
+        y = O.bf(y)
+    # 2 bf16 ulps of the output magnitude: accumulation-order noise can flip each of the (up to 4) rounding points
+    _cmp(out, y, atol=2 ** -7 * max(1.0, float(y.abs().max())) * 0.5, rtol=2 ** -6)
+
+
+@pytest.mark.parametrize("B,H,KVH,Sq,Skv,D,causal,rs", [
+    (2, 16, 16, 577, 577, 64, False, True),      # CLIP (eager: scores rounded to bf16)
+    (1, 16, 16, 2049, 2049, 88, False, False),   # InternVideo2 (d=88 padded to 96 inside the kernel)
+    (1, 8, 8, 1000, 1000, 96, True, False),      # Phi-3.5 prefill
+    (1, 8, 2, 300, 300, 128, True, False),       # Llama-3 GQA
+    (1, 2, 2, 50, 50, 64, False, False),         # single partial tile
+    (1, 4, 4, 1, 130, 96, True, False),          # q_len 1 against a longer cache (bottom-right causal)
+])
+def test_attention_vs_oracle(gvl, B, H, KVH, Sq, Skv, D, causal, rs):
+    g = torch.Generator().manual_seed(Sq + D)
+    q = O.bf(torch.randn(B, Sq, H, D, generator=g))
+    k = O.bf(torch.randn(B, Skv, KVH, D, generator=g))
+    v = O.bf(torch.randn(B, Skv, KVH, D, generator=g))
+    scale = D ** -0.5
+    o = gvl.ops.attention(q.cuda().bfloat16(), k.cuda().bfloat16(), v.cuda().bfloat16(), scale, causal=causal,
+                          round_scores=rs)
+    rep = H // KVH
+    ref = O.attention_core(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3).repeat_interleave(rep, 1),
+                           v.permute(0, 2, 1, 3).repeat_interleave(rep, 1), scale, causal, "bf16",
+                           style="eager" if rs else "flash").permute(0, 2, 1, 3)
+    _cmp(o, ref, atol=2e-2, rtol=2e-2)   # online-softmax block maxima differ from the global max: P rounds differently
+
+
+def test_norm_kernels(gvl):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(577 * 2, 1024, generator=g)
+    w, b = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+    y = gvl.ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    _cmp(y, O.bf(O.layernorm(x, w, b)), atol=2 ** -6, rtol=2 ** -7)       # 1 ulp: fp32 mean/var reduction order
+    xb, wb = O.bf(torch.randn(2049, 1408, generator=g)), O.bf(torch.randn(1408, generator=g))
+    y2 = gvl.ops.rmsnorm(xb.cuda().bfloat16(), wb.cuda().bfloat16(), 1e-6)
+    _cmp(y2, O.rmsnorm(xb, wb, 1e-6, "bf16"), atol=2 ** -6, rtol=2 ** -7)
+    qkv = O.bf(torch.randn(300, 3 * 1408, generator=g))
+    wq, wk = O.bf(1 + 0.1 * torch.randn(1408, generator=g)), O.bf(1 + 0.1 * torch.randn(1408, generator=g))
+    out = gvl.ops.iv2_qk_rmsnorm_(qkv.cuda().bfloat16().clone(), wq.cuda().bfloat16(), wk.cuda().bfloat16())
+    ref = qkv.clone()
+    ref[:, :1408] = O.rmsnorm(qkv[:, :1408], wq, 1e-6, "bf16")
+    ref[:, 1408:2816] = O.rmsnorm(qkv[:, 1408:2816], wk, 1e-6, "bf16")
+    _cmp(out, ref, atol=2 ** -6, rtol=2 ** -7)
+    assert torch.equal(out[:, 2816:].cpu().float(), qkv[:, 2816:])          # v untouched, bit-exact
+
+
+# ------------------------------------------------------------------------------------------- index maps (bit-exact)
+def test_hd_merge_bit_exact_vs_golden_map(gvl, gold_dir):
+    import os
+    z = np.load(os.path.join(gold_dir, "hd_merge_map.npz"))["index_map"]      # produced by the REFERENCE's own method
+    g = torch.Generator().manual_seed(3)
+    hs = O.bf(torch.randn(2, 577, 1024, generator=g))
+    sub = O.bf(torch.randn(4096, generator=g))
+    out = gvl.ops.hd_merge_newline(hs.cuda(), sub.cuda()).float().cpu()
+    flat = hs[:, 1:].reshape(2, -1)
+    for n in range(2):
+        idx = torch.from_numpy(z - 576 * 1024)                                 # golden map was taken for image 1
+        exp = torch.where(idx >= 0, flat[n][idx.clamp(min=0)], sub[(-(torch.from_numpy(z)) - 1).clamp(min=0)])
+        assert torch.equal(out[n], exp)
+    assert torch.equal(out, O.hd_merge_newline(hs[:, 1:], sub))
+    with pytest.raises(ValueError):
+        gvl.ops.hd_merge_newline(torch.zeros(1, 576, 1024, device="cuda"), sub.cuda())
+
+
+def test_pool_concat_splice_im2col_bit_exact(gvl):
+    ops = gvl.ops
+    g = torch.Generator().manual_seed(5)
+    # AdaptiveAvgPool3d([T,4,4]): values chosen so fp32 4x4 sums are exact -> bit-exact comparison is meaningful
+    xv = O.bf(torch.randint(-64, 64, (3, 1 + 2 * 256, 64), generator=g).float() / 8)
+    assert torch.equal(ops.iv2_pool(xv.cuda().bfloat16(), 2).float().cpu(), O.bf(O.pool_temporal(xv, 2)))
+    hs = torch.randint(-64, 64, (2, 577, 1024), generator=g).float()
+    got = ops.clip_pool3(hs.cuda()).float().cpu()
+    _cmp(got, O.bf(O.pool_spatial_llama(hs[:, 1:])), atol=0.0, rtol=2 ** -8)      # /9 is not exact: 1 ulp
+    # embedding gather + visual splice (ids int64, -200 sentinel), both orders
+    table = O.bf(torch.randn(500, 64, generator=g))
+    vis = O.bf(torch.randn(37, 64, generator=g))
+    ids = torch.randint(0, 500, (20,), generator=g)
+    ids[6] = -200
+    for vis_last in (False, True):
+        out = ops.embed_splice(ids.cuda(), 6, table.cuda().bfloat16(), vis.cuda().bfloat16(), vis_last=vis_last)
+        assert torch.equal(out.float().cpu(), O.splice_embeds(ids, table, vis, vis_last=vis_last))
+    # im2col: GEMM over im2col rows == unfold of the reference conv
+    pix = O.bf(torch.randn(2, 3, 2, 224, 224, generator=g))
+    col = ops.im2col_patch14(pix.cuda(), 2, 640).float().cpu()
+    fr = pix.permute(0, 2, 1, 3, 4).reshape(4, 3, 224, 224)
+    ref = torch.nn.functional.unfold(fr, 14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(col[:, :588], ref) and bool((col[:, 588:] == 0).all())
+
+
+def test_rope_and_cache_bit_exact(gvl):
+    g = torch.Generator().manual_seed(9)
+    H, KVH, D, T, maxc = 4, 2, 96, 33, 64
+    r = O.phi35_rope_cfg(D)
+    from gvl import hostlogic
+    cos, sin = hostlogic.longrope_tables(maxc, D, r["base"], r["short_factor"], r["long_factor"], r["max_pos"],
+                                         r["orig_max_pos"], False)
+    qkv = O.bf(torch.randn(T, (H + 2 * KVH) * D, generator=g))
+    kc = torch.zeros(KVH, maxc, D, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    q = gvl.ops.rope_qkv_cache(qkv.cuda().bfloat16(), kc, vc, cos.cuda(), sin.cuda(), H, KVH, D, pos0=5)
+    c, s = cos.float()[5:5 + T], sin.float()[5:5 + T]
+    qr = O.apply_rope(qkv[:, :H * D].reshape(T, H, D), c[:, None], s[:, None], "bf16")
+    kr = O.apply_rope(qkv[:, H * D:(H + KVH) * D].reshape(T, KVH, D), c[:, None], s[:, None], "bf16")
+    assert torch.equal(q.float().cpu().reshape(T, H, D), qr)
+    assert torch.equal(kc[:, 5:5 + T].float().cpu(), kr.transpose(0, 1))
+    assert torch.equal(vc[:, 5:5 + T].float().cpu(), qkv[:, (H + KVH) * D:].reshape(T, KVH, D).transpose(0, 1))
+
+
+# ------------------------------------------------------------------------------------------- stages
+def test_clip_stage_small_and_golden(gvl, gold_dir):
+    import os
+    z = np.load(os.path.join(gold_dir, "clip_tiny.npz"))
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("P:")}
+    pix = torch.from_numpy(z["pix"])
+    m = gvl.model.CLIPVisionModel(P, num_heads=4, num_layers=4, image_size=56)
+    out = m(pix.cuda(), output_hidden_states=True).hidden_states[-2]
+    _cmp(out, O.clip_hidden_states(pix, P, 4, 4, mode="bf16")[-2], atol=0.03, rtol=0.02)
+    _cmp(out, torch.from_numpy(z["hs_m2"]), atol=0.08, rtol=0.05)       # vs the REFERENCE's fp32 output (bf16 noise)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 42, 42), output_hidden_states=True)
+
+
+def test_iv2_stage_small(gvl):
+    P = O.make_iv2_params(dim=64, heads=4, ffn=128, depth=4, frames=2, seed=3, gamma=(0.5, 1.5))
+    pix = torch.randn(2, 3, 2, 224, 224, generator=torch.Generator().manual_seed(4))
+    m = gvl.model.PretrainInternVideo2(P, num_heads=4, depth=4, num_frames=2)
+    out = m(pix.cuda(), None, False, x_vis_return_idx=-2, x_vis_only=True)
+    _cmp(out, O.iv2_forward(pix, P, 4, 4, mode="bf16", x_vis_return_idx=-2), atol=0.03, rtol=0.02)
+    with pytest.raises(NotImplementedError):
+        m(pix.cuda())
+
+
+@pytest.mark.parametrize("arch", ["phi3", "llama"])
+def test_lm_prefill_logits_and_greedy_decode(gvl, arch):
+    kvh = 4 if arch == "phi3" else 2
+    P = O.make_lm_params(arch=arch, dim=256, heads=4, kv_heads=kvh, head_dim=64, ffn=512, layers=2, vocab=1000, seed=5,
+                         std=0.05)
+    rope = O.phi35_rope_cfg(64) if arch == "phi3" else dict(type="plain", base=500000.0, bf16_quirk=True)
+    cfg = dict(arch=arch, layers=2, heads=4, kv_heads=kvh, head_dim=64, eps=1e-5, rope=rope)
+    emb = torch.randn(40, 256, generator=torch.Generator().manual_seed(6)) * 0.5
+    lm = gvl.model.CausalLM(P, arch, 4, kvh, 64, 1e-5, rope, max_ctx=256)
+    logits = lm(inputs_embeds=emb.cuda()[None]).logits[0]
+    _cmp(logits, O.lm_forward(emb, P, cfg, mode="bf16"), atol=1e-2, rtol=2 ** -6)     # north_star: 1e-2 max-abs
+    toks, lg = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=6, return_logits=True)
+    toks_ref, lg_ref = O.greedy_decode(emb, P, cfg, 6, mode="bf16")
+    _cmp(lg[0], lg_ref, atol=1e-2, rtol=2 ** -6)
+    # greedy tokens agree wherever the oracle's top-2 margin exceeds the logit tolerance
+    for t in range(6):
+        top2 = torch.topk(lg_ref[t], 2).values
+        if float(top2[0] - top2[1]) > 2e-2:
+            assert int(toks[0, t]) == toks_ref[t]
+    lm.close()
+
+
+def test_eos_padding_semantics(gvl):
+    P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=1, vocab=300, seed=11,
+                         std=0.05)
+    rope = O.phi35_rope_cfg(64)
+    lm = gvl.model.CausalLM(P, "phi3", 4, 4, 64, 1e-5, rope, max_ctx=128)
+    emb = torch.randn(10, 256, generator=torch.Generator().manual_seed(1)) * 0.5
+    free = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=8)[0].tolist()
+    eos = free[3]
+    first = free.index(eos)
+    got = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=8, eos_token_id=eos, pad_token_id=7)[0].tolist()
+    assert got[:first + 1] == free[:first + 1] and all(t == 7 for t in got[first + 1:])
+    with pytest.raises(ValueError):
+        lm.generate(inputs_embeds=torch.zeros(1, 200, 256, device="cuda"), max_new_tokens=8)
+    lm.close()
+
+
+def test_full_width_single_units_vs_oracle_on_device(gvl):
+    """Full-size widths (1 CLIP image x 23 layers; 1 InternVideo2 segment x 6 blocks; 3 Phi-3.5 layers at S=700), oracle
+    evaluated with torch on the same device to finish in seconds."""
+    dev = "cuda"
+    P = O.make_clip_params(seed=1)
+    pix = torch.randn(1, 3, 336, 336, generator=torch.Generator().manual_seed(2))
+    ref = O.clip_hidden_states(pix.to(dev), {k: v.to(dev) for k, v in P.items()}, 16, 24, mode="bf16", upto=23)[-1]
+    out = gvl.model.CLIPVisionModel(P, 16, 24)(pix.to(dev), output_hidden_states=True).hidden_states[-2]
+    _cmp(out, ref, atol=0.06, rtol=0.02)
+    del P
+    P = O.make_iv2_params(depth=7, seed=3, gamma=(0.05, 0.15))
+    pix = torch.randn(1, 3, 8, 224, 224, generator=torch.Generator().manual_seed(4))
+    ref = O.iv2_forward(pix.to(dev), {k: v.to(dev) for k, v in P.items()}, 16, 7, mode="bf16", x_vis_return_idx=-2)
+    out = gvl.model.PretrainInternVideo2(P, 16, 7, 8)(pix.to(dev), None, False, x_vis_return_idx=-2, x_vis_only=True)
+    _cmp(out, ref, atol=0.06, rtol=0.02)
+    del P
+    P = O.make_lm_params(arch="phi3", layers=3, vocab=32366, seed=7)
+    rope = O.phi35_rope_cfg(96)
+    cfg = dict(arch="phi3", layers=3, heads=32, kv_heads=32, head_dim=96, eps=1e-5, rope=rope)
+    emb = torch.randn(700, 3072, generator=torch.Generator().manual_seed(8)) * 0.05
+    ref = O.lm_forward(emb.to(dev), {k: v.to(dev) for k, v in P.items()}, cfg, mode="bf16")
+    lm = gvl.model.CausalLM(P, "phi3", 32, 32, 96, 1e-5, rope, max_ctx=1024)
+    out = lm(inputs_embeds=emb.to(dev)[None]).logits[0]
+    _cmp(out, ref, atol=1e-2, rtol=2 ** -6)
+    lm.close()
+
+
+def test_pipeline_small_end_to_end(gvl):
+    """encode_images + prepare_multimodal_inputs + generate on a reduced-depth model with production per-segment shapes
+    (1 segment x 8 frames: 156 + 128 + 1 = 285 visual tokens), vs the oracle."""
+    from gvl import synth
+    params, lm_cfg, clip_cfg, iv2_cfg = synth.make_params(
+        "phi3.5", device="cpu", seed=3, lm=dict(synth.PHI35, layers=2, vocab=1000 + 302, dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512),
+        clip=dict(synth.CLIP_L336, layers=3), iv2=dict(synth.IV2_1B, depth=3, gamma=0.1), lm_dtype=torch.float32)
+    m = gvl.model.LLAVA_NEXT_VIDEO(params, llm="phi3.5", num_frames=8, num_segs=1, lm_cfg=lm_cfg, clip_cfg=clip_cfg,
+                                   iv2_cfg=iv2_cfg, max_ctx=512)
+    g = torch.Generator().manual_seed(1234)
+    sp, tp = torch.randn(1, 1, 3, 336, 336, generator=g), torch.randn(1, 8, 3, 224, 224, generator=g)
+    ids = torch.randint(3, 1000, (24,), generator=torch.Generator().manual_seed(7))
+    ids[9] = -200
+    samples = {"spatial_pixel_values": sp, "temporal_pixel_values": tp, "input_ids": [ids.tolist()]}
+    feats = m.encode_images(samples)
+    assert feats.shape == (1, 285, 256)
+    OP = {"clip": params["vision_tower"], "iv2": params["video_encoder"], "sub_GN": params["sub_GN"], "glb_GN": params["glb_GN"]}
+    OP.update({"mm." + k: v for k, v in params["multi_modal_projector"].items()})
+    OP.update({"vp." + k: v for k, v in params["video_projecter"].items()})
+    ocfg = dict(clip_heads=16, clip_layers=3, iv2_heads=16, iv2_depth=3)
+    ref = O.encode_images_phi(sp, tp, OP, ocfg, mode="bf16")
+    _cmp(feats, ref, atol=0.03, rtol=0.03)
+    toks = m.generate(samples, max_new_tokens=4)[0]
+    table = O.bf(params["language_model"]["model.embed_tokens.weight"].float())
+    emb = O.splice_embeds(ids, table, ref[0])
+    lcfg = dict(arch="phi3", layers=2, heads=4, kv_heads=4, head_dim=64, eps=1e-5, rope=O.phi35_rope_cfg(64))
+    toks_ref, lg_ref = O.greedy_decode(emb, params["language_model"], lcfg, 4, mode="bf16")
+    top2 = torch.topk(lg_ref[0], 2).values
+    if float(top2[0] - top2[1]) > 5e-2:
+        assert int(toks[0]) == toks_ref[0]

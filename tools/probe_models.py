@@ -270,14 +270,14 @@ CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+    if os.environ.get("PROBE_CHILD") and len(sys.argv) > 1 and sys.argv[1] in CASES:
         t0 = time.time()
         print("RESULT %s :: %s (%.1fs)" % (sys.argv[1], CASES[sys.argv[1]](), time.time() - t0))
         return
     names = sys.argv[1:] if len(sys.argv) > 1 else list(CASES)
     for name in names:
         try:
-            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=600)
+            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=600, env=dict(os.environ, PROBE_CHILD="1"))
             txt = r.stdout + r.stderr
             if "RESULT" in txt:
                 print(txt[txt.index("RESULT"):].strip())

@@ -172,14 +172,14 @@ CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+    if os.environ.get("PROBE_CHILD") and len(sys.argv) > 1 and sys.argv[1] in CASES:
         t0 = time.time()
         err, scale = CASES[sys.argv[1]]()
         print("RESULT %s err=%.4g scale=%.4g time=%.1fs" % (sys.argv[1], err, scale, time.time() - t0))
         return
     for name in CASES:
         try:
-            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=180)
+            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=180, env=dict(os.environ, PROBE_CHILD="1"))
             lines = [l for l in (r.stdout + r.stderr).splitlines() if l.strip()]
             res = [l for l in lines if l.startswith("RESULT")]
             if res:
