@@ -23,7 +23,7 @@ int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int
 
 int gvl_attention(const void* q, const void* k, const void* v, void* o, const long long* qs, const long long* ks,
                   const long long* vs, const long long* os, int batch, int heads, int kv_heads, int sq, int skv,
-                  int head_dim, float scale, int causal, int round_scores, void* stream) {
+                  int head_dim, float scale, int causal, int round_scores, int o_dim, void* stream) {
     if (!q || !k || !v || !o || !qs || !ks || !vs || !os) return GVL_ERR_ARG;
     AttnArgs a;
     a.q = (const __nv_bfloat16*)q; a.k = (const __nv_bfloat16*)k; a.v = (const __nv_bfloat16*)v;
@@ -33,7 +33,7 @@ int gvl_attention(const void* q, const void* k, const void* v, void* o, const lo
     a.v_bs = vs[0]; a.v_ts = vs[1]; a.v_hs = vs[2];
     a.o_bs = os[0]; a.o_ts = os[1]; a.o_hs = os[2];
     a.batch = batch; a.heads = heads; a.kv_heads = kv_heads; a.sq = sq; a.skv = skv; a.head_dim = head_dim;
-    a.scale = scale; a.causal = causal; a.round_scores = round_scores;
+    a.scale = scale; a.causal = causal; a.round_scores = round_scores; a.o_dim = o_dim;
     return attention_fwd(a, S(stream));
 }
 

@@ -10,6 +10,7 @@
 // Numerics follow the reference: fp32 scores, fp32 softmax statistics, probabilities rounded to
 // bf16 before the P*V product, fp32 output accumulation, one final bf16 rounding.
 #include "gvl_internal.h"
+#include <stdlib.h>
 #include "ptx.cuh"
 
 namespace gvl {
@@ -239,8 +240,9 @@ attn_fwd_kernel(const AttnArgs a) {
     }
     __syncwarp();
     __nv_bfloat16* op = a.o + b * a.o_bs + h * a.o_hs;
-    for (int i = lane; i < 16 * real_ch; i += 32) {
-        const int r = warp * 16 + i / real_ch, c = i % real_ch;
+    const int out_ch = (a.o_dim > 0 ? a.o_dim : d_real) / 8;
+    for (int i = lane; i < 16 * out_ch; i += 32) {
+        const int r = warp * 16 + i / out_ch, c = i % out_ch;
         if (m0 + r < a.sq) {
             uint4 val = *reinterpret_cast<const uint4*>(sQ + r * LDS + c * 8);
             *reinterpret_cast<uint4*>(op + (long long)(m0 + r) * a.o_ts + c * 8) = val;
@@ -270,6 +272,17 @@ int launch_attn(const AttnArgs& a, cudaStream_t stream) {
 int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
     if (a.head_dim % 8 != 0 || a.head_dim > 128 || a.heads % a.kv_heads != 0) return GVL_ERR_ARG;
     if (a.sq <= 0 || a.skv <= 0) return GVL_ERR_ARG;
+    static const bool force_mma = getenv("GVL_ATTN_MMA") != nullptr;   // A/B switch for bring-up / profiling
+    if (!force_mma && attention_tc_supported(a)) {
+        prof_begin(GVL_PROF_ATTN, 4.0 * a.batch * a.heads * (double)a.sq * a.skv * a.head_dim * (a.causal ? 0.5 : 1.0), stream);
+        int rc = attention_tc_fwd(a, stream);
+        prof_end(GVL_PROF_ATTN, stream);
+        return rc;
+    }
+    return attention_mma_fwd(a, stream);
+}
+
+int attention_mma_fwd(const AttnArgs& a, cudaStream_t stream) {
     const int hd = (a.head_dim + 15) / 16 * 16;
     // algorithmic FLOPs: 4*Sq*Skv*D per (batch, head), halved under the causal mask
     prof_begin(GVL_PROF_ATTN, 4.0 * a.batch * a.heads * (double)a.sq * a.skv * a.head_dim * (a.causal ? 0.5 : 1.0), stream);

@@ -53,8 +53,12 @@ struct AttnArgs {
     float scale;
     int causal;        // bottom-right aligned causal mask (flash-attn convention)
     int round_scores;  // 1: round q*k^T to bf16 before softmax (eager bmm path, CLIP)
+    int o_dim = 0;     // columns of each head actually written to o (0 = head_dim); IV2 stores 88 of a padded 96
 };
-int attention_fwd(const AttnArgs& a, cudaStream_t stream);
+int attention_fwd(const AttnArgs& a, cudaStream_t stream);        // dispatch: tcgen05 kernel when the shape allows
+int attention_mma_fwd(const AttnArgs& a, cudaStream_t stream);    // attention.cu  (mma.sync, any head_dim % 8 == 0)
+bool attention_tc_supported(const AttnArgs& a);                   // attention_tc.cu (tcgen05/TMEM/TMA, d in 64/96/128)
+int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 
 // rowops.cu
 int layernorm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows,
@@ -64,7 +68,7 @@ int layernorm_f32_to_f32(const float* x, const float* w, const float* b, float* 
 int rmsnorm_bf16(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, __nv_bfloat16* y,
                  long long ldy, int rows, int cols, float eps, cudaStream_t s);
 int iv2_qk_rmsnorm(__nv_bfloat16* qkv, const __nv_bfloat16* wq, const __nv_bfloat16* wk, int rows,
-                   int dim, float eps, cudaStream_t s);
+                   int dim, float eps, cudaStream_t s, int n_real = 0);
 
 // gather.cu
 int im2col_patch14(const void* pix, int pix_is_f32, __nv_bfloat16* out, int n_img, int chans, int frames,

@@ -56,14 +56,14 @@ Iv2Bufs carve_iv2(const gvl_iv2_weights* w, int n_seg, void* base) {
     b.col = c.take<__nv_bfloat16>((size_t)n_seg * np * w->kpad);
     b.patch = c.take<__nv_bfloat16>((size_t)n_seg * np * w->dim);
     b.h = c.take<__nv_bfloat16>(T * w->dim);
-    b.qkv = c.take<__nv_bfloat16>(T * 3 * w->dim);
+    b.qkv = c.take<__nv_bfloat16>(T * 3 * w->heads * w->head_dim_pad);
     b.attn = c.take<__nv_bfloat16>(T * w->dim);
     b.mid = c.take<__nv_bfloat16>(T * w->ffn);
     b.bytes = c.off + 256;
     return b;
 }
 
-#define CK(expr)                   \
+#define CK(expr)                 \
     do {                           \
         int _rc = (expr);          \
         if (_rc != GVL_OK) return _rc; \
@@ -136,6 +136,8 @@ int gvl_iv2_encode(const gvl_iv2_weights* w, const float* pix, void* x_out, int 
     if (b.bytes > ws_bytes) return GVL_ERR_NOMEM;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int D = w->dim, F = w->ffn, H = w->heads, hd = D / H;
+    const int hdp = w->head_dim_pad, Dp = H * hdp;
+    if (hdp < hd || hdp % 8 != 0 || hdp > 128) return GVL_ERR_ARG;
     const int np = w->frames * 256;
     const int S = np + 1;
     const int T = n_seg * S;
@@ -152,16 +154,17 @@ int gvl_iv2_encode(const gvl_iv2_weights* w, const float* pix, void* x_out, int 
         const gvl_iv2_block& B = w->blocks[l];
         // Block._inner_forward (internvideo2.py:680-684): x += ls1(attn(norm1(x))); x += ls2(mlp(norm2(x)))
         CK(rmsnorm_bf16(x, D, (const __nv_bfloat16*)B.norm1_w, b.h, D, T, D, 1e-6f, s));
-        CK(gemm_bf16(b.h, D, B.qkv_w, D, b.qkv, 3 * D, T, 3 * D, D, nullptr, nullptr, nullptr, 0, GVL_ACT_NONE,
+        // q/k/v leave the GEMM with every head zero-padded hd -> hdp (zero weight rows), see gvl.h
+        CK(gemm_bf16(b.h, D, B.qkv_w, D, b.qkv, 3 * Dp, T, 3 * Dp, D, nullptr, nullptr, nullptr, 0, GVL_ACT_NONE,
                      GVL_RES_NONE, 0, 0, s));
-        CK(iv2_qk_rmsnorm(b.qkv, (const __nv_bfloat16*)B.q_norm_w, (const __nv_bfloat16*)B.k_norm_w, T, D, 1e-6f, s));
+        CK(iv2_qk_rmsnorm(b.qkv, (const __nv_bfloat16*)B.q_norm_w, (const __nv_bfloat16*)B.k_norm_w, T, Dp, 1e-6f, s, D));
         AttnArgs a;
-        a.q = b.qkv; a.k = b.qkv + D; a.v = b.qkv + 2 * D; a.o = b.attn;
-        a.q_bs = a.k_bs = a.v_bs = (long long)S * 3 * D;
-        a.q_ts = a.k_ts = a.v_ts = 3 * D;
-        a.q_hs = a.k_hs = a.v_hs = hd;
+        a.q = b.qkv; a.k = b.qkv + Dp; a.v = b.qkv + 2 * Dp; a.o = b.attn;
+        a.q_bs = a.k_bs = a.v_bs = (long long)S * 3 * Dp;
+        a.q_ts = a.k_ts = a.v_ts = 3 * Dp;
+        a.q_hs = a.k_hs = a.v_hs = hdp;
         a.o_bs = (long long)S * D; a.o_ts = D; a.o_hs = hd;
-        a.batch = n_seg; a.heads = H; a.kv_heads = H; a.sq = S; a.skv = S; a.head_dim = hd;
+        a.batch = n_seg; a.heads = H; a.kv_heads = H; a.sq = S; a.skv = S; a.head_dim = hdp; a.o_dim = hd;
         a.scale = scale; a.causal = 0; a.round_scores = 0;
         CK(attention_fwd(a, s));
         CK(gemm_bf16(b.attn, D, B.proj_w, D, x, D, T, D, D, B.proj_b, (const float*)B.ls1, x, D, GVL_ACT_NONE,

@@ -207,6 +207,11 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
     __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
     return __bfloat1622float2(b);
 }
+__device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2; ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -64,7 +64,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 }
 
 __device__ __forceinline__ void rms_row(const __nv_bfloat16* xr, const __nv_bfloat16* __restrict__ w,
-                                        __nv_bfloat16* yr, int cols, float eps, int lane) {
+                                        __nv_bfloat16* yr, int cols, float eps, int lane, int n_mean = 0) {
     const uint4* x4 = reinterpret_cast<const uint4*>(xr);
     const int nv = cols / 8;
     float ss = 0.f;
@@ -76,7 +76,8 @@ __device__ __forceinline__ void rms_row(const __nv_bfloat16* xr, const __nv_bflo
         f = unpack_bf16(v.z); ss += f.x * f.x + f.y * f.y;
         f = unpack_bf16(v.w); ss += f.x * f.x + f.y * f.y;
     }
-    const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+    // n_mean > 0: the row is zero-padded (IV2 heads stored 88 -> 96) and the mean runs over the real elements
+    const float rstd = rsqrtf(warp_sum(ss) / (n_mean > 0 ? n_mean : cols) + eps);
     const uint4* w4 = reinterpret_cast<const uint4*>(w);
     uint4* y4 = reinterpret_cast<uint4*>(yr);
     for (int i = lane; i < nv; i += 32) {
@@ -100,12 +101,12 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bf
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 qk_rmsnorm_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ wq,
-                  const __nv_bfloat16* __restrict__ wk, int rows, int dim, float eps) {
+                  const __nv_bfloat16* __restrict__ wk, int rows, int dim, float eps, int n_real) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int part = blockIdx.y;  // 0 = q, 1 = k
     __nv_bfloat16* p = qkv + size_t(row) * 3 * dim + size_t(part) * dim;
-    rms_row(p, part == 0 ? wq : wk, p, dim, eps, threadIdx.x & 31);
+    rms_row(p, part == 0 ? wq : wk, p, dim, eps, threadIdx.x & 31, n_real);
 }
 
 }  // namespace
@@ -137,10 +138,10 @@ int rmsnorm_bf16(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, 
 }
 
 int iv2_qk_rmsnorm(__nv_bfloat16* qkv, const __nv_bfloat16* wq, const __nv_bfloat16* wk, int rows, int dim,
-                   float eps, cudaStream_t s) {
+                   float eps, cudaStream_t s, int n_real) {
     if (dim % 8 != 0 || rows <= 0) return GVL_ERR_ARG;
     dim3 grid((rows + ROW_WARPS - 1) / ROW_WARPS, 2);
-    qk_rmsnorm_kernel<<<grid, ROW_WARPS * 32, 0, s>>>(qkv, wq, wk, rows, dim, eps);
+    qk_rmsnorm_kernel<<<grid, ROW_WARPS * 32, 0, s>>>(qkv, wq, wk, rows, dim, eps, n_real);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }

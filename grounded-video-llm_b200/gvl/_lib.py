@@ -49,6 +49,7 @@ class Iv2Block(ctypes.Structure):
 
 class Iv2Weights(ctypes.Structure):
     _fields_ = [("n_blocks", c_i), ("dim", c_i), ("heads", c_i), ("ffn", c_i), ("frames", c_i), ("kpad", c_i),
+                ("head_dim_pad", c_i),
                 ("patch_w", c_vp), ("patch_b", c_vp), ("cls", c_vp), ("pos", c_vp),
                 ("blocks", ctypes.POINTER(Iv2Block))]
 
@@ -72,7 +73,7 @@ _SIGS = {
                             c_i, c_vp]),
     "gvl_attention": (c_i, [c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll),
                             ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
-                            c_vp]),
+                            c_i, c_vp]),
     "gvl_layernorm_f32": (c_i, [c_vp, c_vp, c_vp, c_vp, c_i, c_i, c_f, c_vp]),
     "gvl_rmsnorm_bf16": (c_i, [c_vp, c_ll, c_vp, c_vp, c_ll, c_i, c_i, c_f, c_vp]),
     "gvl_iv2_qk_rmsnorm": (c_i, [c_vp, c_vp, c_vp, c_i, c_i, c_f, c_vp]),

@@ -64,7 +64,7 @@ def _strides3(t_bs, t_ts, t_hs):
     return arr
 
 
-def attention(q, k, v, scale, causal=False, round_scores=False, out=None):
+def attention(q, k, v, scale, causal=False, round_scores=False, out=None, o_dim=0):
     """q [B,Sq,H,D], k/v [B,Skv,KVH,D] (any strides with unit stride on D) -> o [B,Sq,H,D] bf16."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -74,13 +74,13 @@ def attention(q, k, v, scale, causal=False, round_scores=False, out=None):
     B, Sq, H, D = q.shape
     Skv, KVH = k.shape[1], k.shape[2]
     if out is None:
-        out = torch.empty((B, Sq, H, D), dtype=torch.bfloat16, device=q.device)
+        out = torch.empty((B, Sq, H, o_dim if o_dim else D), dtype=torch.bfloat16, device=q.device)
     rc = lib.gvl_attention(_p(q), _p(k), _p(v), _p(out),
                            _strides3(q.stride(0), q.stride(1), q.stride(2)),
                            _strides3(k.stride(0), k.stride(1), k.stride(2)),
                            _strides3(v.stride(0), v.stride(1), v.stride(2)),
                            _strides3(out.stride(0), out.stride(1), out.stride(2)),
-                           B, H, KVH, Sq, Skv, D, float(scale), int(causal), int(round_scores), _stream())
+                           B, H, KVH, Sq, Skv, D, float(scale), int(causal), int(round_scores), int(o_dim), _stream())
     _lib.check(rc, "gvl_attention")
     return out
 

@@ -112,13 +112,26 @@ def pack_iv2(sd, heads, n_blocks_run, frames, device="cuda"):
     D = pw.shape[0]
     ffn = sd["blocks.0.mlp.fc1.weight"].shape[0]
     blocks = (_lib.Iv2Block * n_blocks_run)()
+    hd = D // heads
+    hdp = (hd + 31) // 32 * 32          # 88 -> 96: TMA / tcgen05 friendly head stride; pad rows are exact zeros
+
+    def pad_heads(t, lead):
+        """[lead*heads*hd, ...] -> [lead*heads*hdp, ...] with zeros in each head's pad rows."""
+        if hdp == hd:
+            return t
+        tail = t.shape[1:]
+        t = t.reshape(lead, heads, hd, *tail)
+        out = torch.zeros((lead, heads, hdp) + tuple(tail), dtype=t.dtype, device=t.device)
+        out[:, :, :hd] = t
+        return out.reshape(lead * heads * hdp, *tail)
+
     for i in range(n_blocks_run):
         p = "blocks.%d." % i
         B = blocks[i]
         B.norm1_w = pk.keep(_dev(sd[p + "norm1.weight"], bf, device))
-        B.qkv_w = pk.keep(_dev(sd[p + "attn.qkv.weight"], bf, device))
-        B.q_norm_w = pk.keep(_dev(sd[p + "attn.q_norm.weight"], bf, device))
-        B.k_norm_w = pk.keep(_dev(sd[p + "attn.k_norm.weight"], bf, device))
+        B.qkv_w = pk.keep(_dev(pad_heads(sd[p + "attn.qkv.weight"], 3), bf, device))
+        B.q_norm_w = pk.keep(_dev(pad_heads(sd[p + "attn.q_norm.weight"], 1), bf, device))
+        B.k_norm_w = pk.keep(_dev(pad_heads(sd[p + "attn.k_norm.weight"], 1), bf, device))
         B.proj_w = pk.keep(_dev(sd[p + "attn.proj.weight"], bf, device))
         B.proj_b = pk.keep(_dev(sd[p + "attn.proj.bias"], bf, device))
         B.ls1 = pk.keep(_dev(sd[p + "ls1.gamma"].to(bf), f32, device))
@@ -130,6 +143,7 @@ def pack_iv2(sd, heads, n_blocks_run, frames, device="cuda"):
         B.ls2 = pk.keep(_dev(sd[p + "ls2.gamma"].to(bf), f32, device))
     w = _lib.Iv2Weights()
     w.n_blocks, w.dim, w.heads, w.ffn, w.frames = n_blocks_run, D, heads, ffn, frames
+    w.head_dim_pad = hdp
     kreal = pw[0].numel()
     w.kpad = (kreal + 63) // 64 * 64
     w.patch_w = pk.keep(_dev(_pad_k(pw.reshape(D, -1).float(), w.kpad), bf, device))

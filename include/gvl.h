@@ -55,7 +55,8 @@ int gvl_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int
 int gvl_attention(const void* q, const void* k, const void* v, void* o,
                   const long long* q_strides /*[3] batch,token,head*/, const long long* k_strides,
                   const long long* v_strides, const long long* o_strides, int batch, int heads, int kv_heads,
-                  int sq, int skv, int head_dim, float scale, int causal, int round_scores, void* stream);
+                  int sq, int skv, int head_dim, float scale, int causal, int round_scores, int o_dim /*0 = head_dim*/,
+                  void* stream);
 
 /* nn.LayerNorm on an fp32 stream, output rounded to bf16 (modeling_clip.py:351-353, 824-826). */
 int gvl_layernorm_f32(const float* x, const float* w, const float* b, void* y_bf16, int rows, int cols, float eps,
@@ -155,6 +156,9 @@ typedef struct {
 typedef struct {
     int n_blocks;                /* blocks to run (39: x_vis_return_idx=-2, internvideo2.py:1028-1030) */
     int dim, heads, ffn, frames, kpad;
+    int head_dim_pad;            /* head_dim (88) rounded up to a multiple of 32 (96): qkv_w is [3*heads*head_dim_pad, D]
+                                    with zero rows at the pad positions, q/k norm weights are [heads*head_dim_pad] with
+                                    zeros there, so q/k/v come out of the GEMM already padded for the tcgen05 attention */
     const void *patch_w, *patch_b; /* bf16 [D,kpad], [D] */
     const void* cls;             /* bf16 [D] */
     const void* pos;             /* bf16 [1+frames*256, D] */
