@@ -41,6 +41,7 @@ __device__ __forceinline__ float dot8(uint4 w, uint4 x) {
     return s;
 }
 
+#if 0  // first-generation GEMV (kept for reference; superseded by gemv.cu)
 constexpr int GEMV_THREADS = 256;
 constexpr int GEMV_MAXM = 4;
 
@@ -163,6 +164,8 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* _
         }
     }
 }
+
+#endif
 
 // ---------------------------------------------------------------- decode attention
 constexpr int DA_THREADS = 128;
@@ -425,6 +428,7 @@ step_end_kernel(const float* __restrict__ logits, int n, DecodeState* st, long l
 
 }  // namespace
 
+#if 0  // superseded by gemv.cu
 int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, void* out, int ldo, int M, int N,
               int K, const __nv_bfloat16* norm_w, float eps, const __nv_bfloat16* bias,
               const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s) {
@@ -459,6 +463,7 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
+#endif
 
 size_t decode_attention_workspace(int heads, int head_dim, int max_ctx) {
     const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;

@@ -24,7 +24,8 @@ namespace gvl {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 template <int BN>
 struct GemmCfg {
@@ -82,7 +83,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);
+            ptx::mbar_init(tempty_bar(s), GEMM_EPI_WARPS);
         }
         ptx::fence_mbar_init();
     }
@@ -148,10 +149,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int col_half = (warp - 2) / 4;  // warps 2..5 take the first half of the chunks, 6..9 the second
         int as = 0;
         uint32_t aphase = 0;
         constexpr int NCHUNK = (ACT == ACT_SWIGLU) ? BN / 64 : BN / 32;
         constexpr int BN_OUT = (ACT == ACT_SWIGLU) ? BN / 2 : BN;
+        constexpr int CH_PER = NCHUNK / (GEMM_EPI_WARPS / 4);
+        const int chunk_lo = col_half * CH_PER, chunk_hi = chunk_lo + CH_PER;
         const int n_out_total = (ACT == ACT_SWIGLU) ? p.N / 2 : p.N;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m_idx = t / p.num_n_tiles;
@@ -162,7 +166,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const bool row_ok = row < p.M;
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < NCHUNK; ++c) {
+            for (int c = chunk_lo; c < chunk_hi; ++c) {
                 uint32_t acc[32];
                 float v[32];
                 const int col_in = n_idx * BN + c * 32;       // column in the GEMM's N space
