@@ -18,6 +18,7 @@
 // Numerics as in attention.cu / the reference flash-attn path: fp32 scores, fp32 statistics, P rounded to bf16
 // before P@V, fp32 accumulation, one final rounding. The row sum uses the un-rounded fp32 probabilities (FA2).
 #include <cuda.h>
+#include <type_traits>
 #include "gvl_internal.h"
 #include "ptx.cuh"
 
@@ -81,7 +82,7 @@ struct AtcParams {
     int round_scores;
 };
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, bool ROUND>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AtcParams p) {
@@ -223,21 +224,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int n0 = j * TK;
             const bool need_mask = (n0 + TK > p.skv) || (CAUSAL && (n0 + TK - 1 > m0 + q * 32 + causal_off));
             const int col_lim = CAUSAL ? min(p.skv, row + causal_off + 1) : p.skv;   // valid cols: [0, col_lim)
-            // pass 1: row max of this tile
-            float mx = -INFINITY;
+            // pass 1: row max of this tile. The masked variant is a separate instantiation so that full tiles
+            // (all but the last / diagonal ones) carry no compare/select instructions at all.
+            auto pass1 = [&](auto mask_tag) -> float {
+                constexpr bool MASK = decltype(mask_tag)::value;
+                float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tS + c * 32, r);
-                ptx::tmem_wait_ld();
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tS + c * 32, r);
+                    ptx::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(r[i]);
-                    if (p.round_scores) x = bf16r(x);
-                    if (need_mask && (n0 + c * 32 + i >= col_lim)) x = -INFINITY;
-                    mx = fmaxf(mx, x);
+                    for (int i = 0; i < 32; i += 2) {
+                        float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+                        if (ROUND) { x0 = bf16r(x0); x1 = bf16r(x1); }
+                        if (MASK) {
+                            if (n0 + c * 32 + i >= col_lim) x0 = -INFINITY;
+                            if (n0 + c * 32 + i + 1 >= col_lim) x1 = -INFINITY;
+                        }
+                        mx0 = fmaxf(mx0, x0);
+                        mx1 = fmaxf(mx1, x1);
+                    }
                 }
-            }
+                return fmaxf(mx0, mx1);
+            };
+            const float mx = need_mask ? pass1(std::true_type{}) : pass1(std::false_type{});
             const float m_tile = mx * p.scale_log2;
             // lazy rescale: keep the stale reference max unless it would let P grow beyond 2^RESCALE_LOG2
             float factor = 1.0f;
@@ -271,29 +282,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             // pass 2: P = exp2(s * scale_log2 - m_used), row sum, bf16 P back into TMEM over S
             const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
-            float acc = 0.f;
+            auto pass2 = [&](auto mask_tag) -> float {
+                constexpr bool MASK = decltype(mask_tag)::value;
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tS + c * 32, r);
-                ptx::tmem_wait_ld();
-                uint32_t pk[16];
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tS + c * 32, r);
+                    ptx::tmem_wait_ld();
+                    uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x0 = __uint_as_float(r[2 * i]), x1 = __uint_as_float(r[2 * i + 1]);
-                    if (p.round_scores) { x0 = bf16r(x0); x1 = bf16r(x1); }
-                    float p0 = fast_exp2(fmaf(x0, p.scale_log2, neg_m));
-                    float p1 = fast_exp2(fmaf(x1, p.scale_log2, neg_m));
-                    if (need_mask) {
-                        if (n0 + c * 32 + 2 * i >= col_lim) p0 = 0.f;
-                        if (n0 + c * 32 + 2 * i + 1 >= col_lim) p1 = 0.f;
+                    for (int i = 0; i < 16; ++i) {
+                        float x0 = __uint_as_float(r[2 * i]), x1 = __uint_as_float(r[2 * i + 1]);
+                        if (ROUND) { x0 = bf16r(x0); x1 = bf16r(x1); }
+                        float p0 = fast_exp2(fmaf(x0, p.scale_log2, neg_m));
+                        float p1 = fast_exp2(fmaf(x1, p.scale_log2, neg_m));
+                        if (MASK) {
+                            if (n0 + c * 32 + 2 * i >= col_lim) p0 = 0.f;
+                            if (n0 + c * 32 + 2 * i + 1 >= col_lim) p1 = 0.f;
+                        }
+                        acc0 += p0;
+                        acc1 += p1;
+                        pk[i] = pack_bf16(p0, p1);
                     }
-                    acc += p0 + p1;
-                    pk[i] = pack_bf16(p0, p1);
+                    ptx::tmem_st_32x16(tS + c * 16, pk);
                 }
-                ptx::tmem_st_32x16(tS + c * 16, pk);
-            }
-            l_sum += acc;
+                return acc0 + acc1;
+            };
+            l_sum += need_mask ? pass2(std::true_type{}) : pass2(std::false_type{});
             ptx::tmem_wait_st();
             ptx::tc_fence_before();
             __syncwarp();
@@ -368,15 +384,16 @@ int make_tmap_4d(CUtensorMap* tm, const void* ptr, int D, int tokens, int heads,
     return r == CUDA_SUCCESS ? GVL_OK : GVL_ERR_DRIVER;
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, bool ROUND = false>
 int launch_tc(const AttnArgs& a, cudaStream_t stream) {
+    if (!ROUND && a.round_scores) return launch_tc<HD, CAUSAL, true>(a, stream);
     using Cfg = AtcCfg<HD>;
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = make_tmap_4d(&tq, a.q, HD, a.sq, a.heads, a.batch, a.q_ts, a.q_hs, a.q_bs)) != GVL_OK) return rc;
     if ((rc = make_tmap_4d(&tk, a.k, HD, a.skv, a.kv_heads, a.batch, a.k_ts, a.k_hs, a.k_bs)) != GVL_OK) return rc;
     if ((rc = make_tmap_4d(&tv, a.v, HD, a.skv, a.kv_heads, a.batch, a.v_ts, a.v_hs, a.v_bs)) != GVL_OK) return rc;
-    auto kern = attn_tc_kernel<HD, CAUSAL>;
+    auto kern = attn_tc_kernel<HD, CAUSAL, ROUND>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GVL_ERR_CUDA;

@@ -198,8 +198,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }  // namespace ptx
 
 // ---------------------------------------------------------------- small numeric helpers
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// Round-to-bf16 and back. Deliberately goes through the PACKED conversion (SASS F2FP.BF16.F32.PACK_AB, ALU pipe)
+// and a shift instead of the scalar F2F.BF16.F32, which issues on the 16-lane/clk XU pipe together with MUFU:
+// ncu showed the softmax / GEMM epilogues XU-bound on these conversions (profiles/r1_attention_tc.md).
+__device__ __forceinline__ float bf16r(float x) { return __uint_as_float(pack_bf16(x, 0.f) << 16); }
+__device__ __forceinline__ uint32_t pack_bf16_unused_(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
