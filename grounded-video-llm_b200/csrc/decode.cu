@@ -179,6 +179,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
                    int heads, int kv_heads, int max_ctx, float scale) {
     constexpr int EPL = D / 4;  // elements per lane
     constexpr int VPL = EPL / 8;
+    pdl_launch_dependents();
+    pdl_wait();
     const int ctx = *ctx_len_dev;  // tokens in the cache INCLUDING the one appended this step
     const int h = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
     const int hk = h / (heads / kv_heads);
@@ -291,6 +293,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
 
 // grid = heads, block = D threads
 __global__ void decode_attn_combine(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int nsplit, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int h = blockIdx.x, d = threadIdx.x;
     const float* base = ws + (size_t)h * nsplit * (D + 2);
     float M = -INFINITY;
@@ -342,6 +346,8 @@ argmax_kernel(const float* __restrict__ logits, int n, long long* __restrict__ o
 // x = embed[cur_token]; also bumps nothing. One CTA.
 __global__ void embed_token_kernel(const __nv_bfloat16* __restrict__ table, const DecodeState* __restrict__ st,
                                    __nv_bfloat16* __restrict__ x, int dim) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long tok = st->cur_token;
     const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tok * dim);
     for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) reinterpret_cast<uint4*>(x)[i] = src[i];
@@ -354,6 +360,8 @@ __global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_b
                                    const DecodeState* __restrict__ st, int heads, int kv_heads, int D, int max_ctx) {
     const int half = D / 2;
     const int total = (heads + 2 * kv_heads) * half;
+    pdl_launch_dependents();
+    pdl_wait();
     const int pos = st->ctx_len;  // slot == position (single unpadded sequence)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int hh = i / half, j = i % half;
@@ -381,7 +389,11 @@ __global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_b
 
 // After the per-layer rope kernels of a step: attention must see ctx_len+1 tokens. We keep two counters:
 // ctx_len (tokens already in the cache = position of the token being processed) and attn_len = ctx_len+1.
-__global__ void step_begin_kernel(DecodeState* st) { st->attn_len = st->ctx_len + 1; }
+__global__ void step_begin_kernel(DecodeState* st) {
+    pdl_launch_dependents();
+    pdl_wait();
+    st->attn_len = st->ctx_len + 1;
+}
 
 // greedy pick + bookkeeping: tokens_out[step] = argmax (or pad after EOS), cur_token = it, ctx_len++, step++.
 __global__ void __launch_bounds__(1024)
@@ -389,6 +401,8 @@ step_end_kernel(const float* __restrict__ logits, int n, DecodeState* st, long l
                 float* __restrict__ logits_out, long long eos_id, long long pad_id) {
     __shared__ float s_v[32];
     __shared__ int s_i[32];
+    pdl_launch_dependents();
+    pdl_wait();
     float best = -INFINITY;
     int bi = 0x7fffffff;
     const int step = st->step;
@@ -475,13 +489,13 @@ int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv
                      float scale, cudaStream_t s) {
     const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;
     dim3 grid(heads, nsplit);
-    if (head_dim == 64) decode_attn_kernel<64><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
-    else if (head_dim == 96) decode_attn_kernel<96><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
-    else if (head_dim == 128) decode_attn_kernel<128><<<grid, DA_THREADS, 0, s>>>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    if (head_dim == 64) launch_k(decode_attn_kernel<64>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    else if (head_dim == 96) launch_k(decode_attn_kernel<96>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    else if (head_dim == 128) launch_k(decode_attn_kernel<128>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
     else return GVL_ERR_ARG;
     g_launch_count++;
     if (cudaGetLastError() != cudaSuccess) return GVL_ERR_CUDA;
-    decode_attn_combine<<<heads, head_dim, 0, s>>>(ws, o, nsplit, head_dim);
+    launch_k(decode_attn_combine, dim3(heads), dim3(head_dim), 0, s, ws, o, nsplit, head_dim);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
@@ -493,7 +507,7 @@ int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s) {
 }
 
 int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, cudaStream_t s) {
-    embed_token_kernel<<<1, 256, 0, s>>>(table, st, x, dim);
+    launch_k(embed_token_kernel, dim3(1), dim3(256), 0, s, table, st, x, dim);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
@@ -502,20 +516,20 @@ int rope_decode(const __nv_bfloat16* qkv, __nv_bfloat16* q_out, __nv_bfloat16* k
                 const __nv_bfloat16* cosb, const __nv_bfloat16* sinb, const DecodeState* st, int heads, int kv_heads,
                 int D, int max_ctx, cudaStream_t s) {
     const int total = (heads + 2 * kv_heads) * (D / 2);
-    rope_decode_kernel<<<(total + 255) / 256, 256, 0, s>>>(qkv, q_out, k_cache, v_cache, cosb, sinb, st, heads, kv_heads, D, max_ctx);
+    launch_k(rope_decode_kernel, dim3((total + 255) / 256), dim3(256), 0, s, qkv, q_out, k_cache, v_cache, cosb, sinb, st, heads, kv_heads, D, max_ctx);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
 
 int step_begin(DecodeState* st, cudaStream_t s) {
-    step_begin_kernel<<<1, 1, 0, s>>>(st);
+    launch_k(step_begin_kernel, dim3(1), dim3(1), 0, s, st);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
 
 int step_end(const float* logits, int n, DecodeState* st, long long* tokens_out, float* logits_out, long long eos_id,
              long long pad_id, cudaStream_t s) {
-    step_end_kernel<<<1, 1024, 0, s>>>(logits, n, st, tokens_out, logits_out, eos_id, pad_id);
+    launch_k(step_end_kernel, dim3(1), dim3(1024), 0, s, logits, n, st, tokens_out, logits_out, eos_id, pad_id);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }

@@ -279,6 +279,67 @@ __global__ void rope_cache_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bf
     }
 }
 
+// 128-bit vectorised variant (head_dim % 16 == 0): one thread owns 8 consecutive elements j..j+7 of the first half
+// of a head and their partners j+D/2.. of the second half; same arithmetic and rounding points as above.
+__device__ __forceinline__ void rope8(const uint4& a, const uint4& b, const uint4& c1, const uint4& s1, const uint4& c2,
+                                      const uint4& s2, uint4& y1, uint4& y2) {
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+    const uint32_t* pc1 = reinterpret_cast<const uint32_t*>(&c1);
+    const uint32_t* ps1 = reinterpret_cast<const uint32_t*>(&s1);
+    const uint32_t* pc2 = reinterpret_cast<const uint32_t*>(&c2);
+    const uint32_t* ps2 = reinterpret_cast<const uint32_t*>(&s2);
+    uint32_t* o1 = reinterpret_cast<uint32_t*>(&y1);
+    uint32_t* o2 = reinterpret_cast<uint32_t*>(&y2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 x1 = unpack_bf16(pa[i]), x2 = unpack_bf16(pb[i]);
+        const float2 cc1 = unpack_bf16(pc1[i]), ss1 = unpack_bf16(ps1[i]);
+        const float2 cc2 = unpack_bf16(pc2[i]), ss2 = unpack_bf16(ps2[i]);
+        o1[i] = pack_bf16(bf16r(x1.x * cc1.x) + bf16r(-x2.x * ss1.x), bf16r(x1.y * cc1.y) + bf16r(-x2.y * ss1.y));
+        o2[i] = pack_bf16(bf16r(x2.x * cc2.x) + bf16r(x1.x * ss2.x), bf16r(x2.y * cc2.y) + bf16r(x1.y * ss2.y));
+    }
+}
+
+__global__ void rope_cache_vec_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+                                      __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                                      const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
+                                      const int* __restrict__ positions, int tokens, int heads, int kv_heads, int D,
+                                      int pos0, int max_ctx) {
+    const int half = D / 2;
+    const int cph = half / 8;                          // 8-element chunks per half head
+    const int per_tok = (heads + 2 * kv_heads) * cph;
+    const long long total = (long long)tokens * per_tok;
+    const int ld = (heads + 2 * kv_heads) * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = int(i / per_tok);
+        const int r = int(i % per_tok);
+        const int hh = r / cph, j = (r % cph) * 8;
+        const int slot = pos0 + t;
+        const int pos = positions ? positions[t] : slot;
+        const __nv_bfloat16* src = qkv + (size_t)t * ld + (size_t)hh * D;
+        const uint4 a = *reinterpret_cast<const uint4*>(src + j);
+        const uint4 b = *reinterpret_cast<const uint4*>(src + j + half);
+        if (hh < heads + kv_heads) {
+            const __nv_bfloat16* cp = cosb + (size_t)pos * D;
+            const __nv_bfloat16* sp = sinb + (size_t)pos * D;
+            uint4 y1, y2;
+            rope8(a, b, __ldg(reinterpret_cast<const uint4*>(cp + j)), __ldg(reinterpret_cast<const uint4*>(sp + j)),
+                  __ldg(reinterpret_cast<const uint4*>(cp + j + half)), __ldg(reinterpret_cast<const uint4*>(sp + j + half)),
+                  y1, y2);
+            __nv_bfloat16* dst = (hh < heads) ? q_out + (size_t)t * heads * D + (size_t)hh * D
+                                              : k_cache + ((size_t)(hh - heads) * max_ctx + slot) * D;
+            *reinterpret_cast<uint4*>(dst + j) = y1;
+            *reinterpret_cast<uint4*>(dst + j + half) = y2;
+        } else {
+            __nv_bfloat16* dst = v_cache + ((size_t)(hh - heads - kv_heads) * max_ctx + slot) * D;
+            *reinterpret_cast<uint4*>(dst + j) = a;
+            *reinterpret_cast<uint4*>(dst + j + half) = b;
+        }
+    }
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     long long cap = (long long)num_sms() * 16;
@@ -354,6 +415,12 @@ int rope_qkv_cache(const __nv_bfloat16* qkv, __nv_bfloat16* q_out, __nv_bfloat16
                    const __nv_bfloat16* cos, const __nv_bfloat16* sin, const int* positions, int tokens, int heads,
                    int kv_heads, int head_dim, int pos0, int max_ctx, cudaStream_t s) {
     if (head_dim % 2 != 0 || pos0 + tokens > max_ctx) return GVL_ERR_ARG;
+    if (head_dim % 16 == 0) {
+        const long long totv = (long long)tokens * (heads + 2 * kv_heads) * (head_dim / 16);
+        rope_cache_vec_kernel<<<grid_for(totv, 256), 256, 0, s>>>(qkv, q_out, k_cache, v_cache, cos, sin, positions,
+                                                                  tokens, heads, kv_heads, head_dim, pos0, max_ctx);
+        GVL_LAUNCH_CHECK();
+    }
     const long long total = (long long)tokens * (heads + 2 * kv_heads) * (head_dim / 2);
     rope_cache_kernel<<<grid_for(total, 256), 256, 0, s>>>(qkv, q_out, k_cache, v_cache, cos, sin, positions, tokens,
                                                           heads, kv_heads, head_dim, pos0, max_ctx);

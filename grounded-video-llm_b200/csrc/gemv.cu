@@ -85,6 +85,9 @@ gemv2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* 
     // ---- weights first: their DRAM latency overlaps the prologue below
     bool have = false;
     if (gw < n_units) { load_batch(gw, 0); have = true; }
+    // PDL: let the next kernel of the chain get scheduled, then wait until the producer of x has completed.
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- stage x (with optional RMSNorm, rounding identical to rmsnorm_bf16)
     float ss[MT];
@@ -207,7 +210,8 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
                 return GVL_ERR_CUDA;                                                                                  \
             max_set = smem;                                                                                           \
         }                                                                                                             \
-        kern<<<grid, GV_THREADS, smem, s>>>(x, ldx, W, ldw, out, ldo, N, K, norm_w, eps, bias, residual, ldr, out_f32); \
+        if (launch_k(kern, dim3(grid), dim3(GV_THREADS), smem, s, x, ldx, W, ldw, out, ldo, N, K, norm_w, eps, bias,    \
+                     residual, ldr, out_f32) != cudaSuccess) return GVL_ERR_CUDA;                                       \
     } while (0)
     if (act == 3) {
         switch (M) { case 1: GV_LAUNCH(1, true); break; case 2: GV_LAUNCH(2, true); break;

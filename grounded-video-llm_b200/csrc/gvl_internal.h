@@ -22,6 +22,28 @@ extern long long g_launch_count;  // kernels launched by this library (bench.py:
 
 int num_sms();
 
+// Programmatic dependent launch (PDL) for the decode chain: when g_pdl is set, kernels are launched with
+// programmaticStreamSerialization so that kernel N+1 is scheduled while kernel N drains; every such kernel calls
+// pdl_wait() (griddepcontrol.wait) before it touches anything its predecessor wrote. Weight prefetches are issued
+// before the wait, which hides launch latency and the first DRAM round trip of the weight stream.
+extern bool g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (g_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // profile.cu -- optional CUDA-event timing per kernel family (off by default)
 #define GVL_PROF_GEMM 0
 #define GVL_PROF_ATTN 1

@@ -38,6 +38,7 @@ struct gvl_lm {
     bool warmed = false;
     long long g_eos = 0, g_pad = 0;
     bool use_graph = true;
+    bool use_pdl = true;
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
     __nv_bfloat16* kcache(int l) const { return kv + (size_t)l * kv_layer_elems(); }
@@ -79,8 +80,8 @@ int ensure_prefill_ws(gvl_lm* lm, int S) {
 }
 
 // One decode step on `s` (graph-capturable: no host-dependent arguments change between steps).
-int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
-                        cudaStream_t s) {
+int enqueue_decode_step_impl(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id,
+                             long long pad_id, cudaStream_t s) {
     const gvl_lm_weights& w = lm->w;
     const int D = w.dim, H = w.heads, KVH = w.kv_heads, hd = w.head_dim, F = w.ffn;
     const int qkv_n = (H + 2 * KVH) * hd;
@@ -107,6 +108,15 @@ int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, lo
                  s));
     CK(step_end(lm->dlogits, w.vocab, lm->st, tokens_out, logits_out, eos_id, pad_id, s));
     return GVL_OK;
+}
+
+// PDL is enabled for the decode chain only (every kernel in it starts with pdl_wait()).
+int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
+                        cudaStream_t s) {
+    g_pdl = lm->use_pdl;
+    const int rc = enqueue_decode_step_impl(lm, tokens_out, logits_out, eos_id, pad_id, s);
+    g_pdl = false;
+    return rc;
 }
 
 }  // namespace

@@ -197,6 +197,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 }  // namespace ptx
 
+// programmatic dependent launch (no-ops when the kernel was launched without the PDL attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small numeric helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

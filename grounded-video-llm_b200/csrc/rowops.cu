@@ -13,6 +13,7 @@
 namespace gvl {
 
 long long g_launch_count = 0;
+bool g_pdl = false;
 
 namespace {
 
