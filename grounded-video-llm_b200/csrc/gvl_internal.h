@@ -61,6 +61,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo
               const void* bias, const float* gamma, const void* residual, int ldr, int act, int res,
               int out_f32, int bn_hint, cudaStream_t stream);
 
+// gemm_tcgen05_2cta.cu (cta_group::2, 256x256 tiles per CTA pair; same contract, N tile fixed at 256)
+int gemm_bf16_2cta(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                   const void* bias, const float* gamma, const void* residual, int ldr, int act, int res, int out_f32,
+                   cudaStream_t stream);
+
 // attention.cu  (q/k/v: bf16, element strides given per token and per head)
 struct AttnArgs {
     const __nv_bfloat16* q;
