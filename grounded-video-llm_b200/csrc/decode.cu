@@ -169,14 +169,43 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* _
 
 // ---------------------------------------------------------------- decode attention
 constexpr int DA_THREADS = 128;
-constexpr int DA_CHUNK = 256;  // context tokens per CTA
+constexpr int DA_CHUNK = 128;  // context tokens per CTA
+
+// Last-arriving split of a head merges the per-split (max, sum, partial-output) triples (flash-decoding combine),
+// so the whole single-query attention is ONE launch. counters[h] is self-resetting.
+template <int D>
+__device__ __forceinline__ void da_finish(float* ws, int* counters, __nv_bfloat16* o_out, int h, int nsplit, int tid) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&counters[h], 1) == nsplit - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = ws + (size_t)h * nsplit * (D + 2);
+    if (tid < D) {
+        float M = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * (D + 2)));
+        float num = 0.f, den = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float* r = base + (size_t)s * (D + 2);
+            const float m = __ldcg(r);
+            if (m == -INFINITY) continue;
+            const float wgt = __expf(m - M);
+            num += wgt * __ldcg(r + 2 + tid);
+            den += wgt * __ldcg(r + 1);
+        }
+        o_out[(size_t)h * D + tid] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+    }
+    if (tid == 0) counters[h] = 0;
+}
 
 // grid (heads, max_splits). 4 lanes share one token (D/4 elements each); 32 tokens per CTA iteration.
 template <int D>
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                   const __nv_bfloat16* __restrict__ vc, float* __restrict__ ws, const int* __restrict__ ctx_len_dev,
-                   int heads, int kv_heads, int max_ctx, float scale) {
+                   const __nv_bfloat16* __restrict__ vc, float* ws, const int* __restrict__ ctx_len_dev,
+                   int heads, int kv_heads, int max_ctx, float scale, int* counters, __nv_bfloat16* o_out) {
     constexpr int EPL = D / 4;  // elements per lane
     constexpr int VPL = EPL / 8;
     pdl_launch_dependents();
@@ -189,6 +218,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (t0 >= ctx) {
         if (tid == 0) { wrow[0] = -INFINITY; wrow[1] = 0.f; }
+        da_finish<D>(ws, counters, o_out, h, nsplit, tid);
         return;
     }
     const int t1 = min(t0 + DA_CHUNK, ctx);
@@ -289,6 +319,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         wrow[0] = bmax;
         wrow[1] = l;
     }
+    da_finish<D>(ws, counters, o_out, h, nsplit, tid);
 }
 
 // grid = heads, block = D threads
@@ -479,25 +510,26 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
 }
 #endif
 
+// workspace: [heads][nsplit][D+2] fp32 partials followed by [heads] int32 arrival counters.
+// The counters must be ZERO before the first call (gvl_lm_create memsets them; they reset themselves afterwards).
 size_t decode_attention_workspace(int heads, int head_dim, int max_ctx) {
     const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;
-    return (size_t)heads * nsplit * (head_dim + 2) * sizeof(float);
+    return (size_t)heads * nsplit * (head_dim + 2) * sizeof(float) + (size_t)heads * sizeof(int);
 }
 
 int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv_bfloat16* vc, __nv_bfloat16* o,
                      float* ws, const int* ctx_len_dev, int heads, int kv_heads, int head_dim, int max_ctx,
                      float scale, cudaStream_t s) {
     const int nsplit = (max_ctx + DA_CHUNK - 1) / DA_CHUNK;
+    int* counters = reinterpret_cast<int*>(ws + (size_t)heads * nsplit * (head_dim + 2));
     dim3 grid(heads, nsplit);
-    if (head_dim == 64) launch_k(decode_attn_kernel<64>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
-    else if (head_dim == 96) launch_k(decode_attn_kernel<96>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
-    else if (head_dim == 128) launch_k(decode_attn_kernel<128>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale);
+    cudaError_t e;
+    if (head_dim == 64) e = launch_k(decode_attn_kernel<64>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale, counters, o);
+    else if (head_dim == 96) e = launch_k(decode_attn_kernel<96>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale, counters, o);
+    else if (head_dim == 128) e = launch_k(decode_attn_kernel<128>, grid, dim3(DA_THREADS), 0, s, q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale, counters, o);
     else return GVL_ERR_ARG;
     g_launch_count++;
-    if (cudaGetLastError() != cudaSuccess) return GVL_ERR_CUDA;
-    launch_k(decode_attn_combine, dim3(heads), dim3(head_dim), 0, s, ws, o, nsplit, head_dim);
-    g_launch_count++;
-    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? GVL_OK : GVL_ERR_CUDA;
 }
 
 int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s) {

@@ -384,7 +384,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo
     {
         static const char* env = getenv("GVL_GEMM_2CTA");
         const long tiles2 = long((M + 255) / 256) * ((N + 255) / 256);
-        const bool want = env ? (env[0] == '1') : false;
+        const bool want = env ? (env[0] == '1') : true;
         if (want && BN == 256 && bn_hint != 128 && tiles2 >= num_sms() / 2) {
             prof_begin(GVL_PROF_GEMM, 2.0 * M * (double)N * K, stream);
             int rc2 = gemm_bf16_2cta(A, lda, W, ldw, out, ldo, M, N, K, bias, gamma, residual, ldr, act, res, out_f32, stream);

@@ -148,6 +148,7 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
         cudaEventCreateWithFlags(&lm->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&lm->ev_out, cudaEventDisableTiming) != cudaSuccess) { rc = GVL_ERR_CUDA; goto fail; }
     cudaMemset(lm->st, 0, sizeof(DecodeState));
+    cudaMemset(lm->da_ws, 0, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx));
     *out = lm;
     return GVL_OK;
 fail:
@@ -268,7 +269,7 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
             if (e != cudaSuccess) return GVL_ERR_CUDA;
             lm->g_logits = lbuf; lm->g_eos = eos_id; lm->g_pad = pad_id;
         }
-        const long long per_step = 2 + (long long)lm->w.n_layers * 7 + 2;
+        const long long per_step = 2 + (long long)lm->w.n_layers * 6 + 2;
         for (int i = 0; i < n_steps; ++i) {
             CU(cudaGraphLaunch(lm->graph, s));
             g_launch_count += per_step;

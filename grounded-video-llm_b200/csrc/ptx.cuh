@@ -223,8 +223,21 @@ __device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2; ex2(-inf
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Exact-erf GELU (nn.GELU default) for a bf16-rounded input, result rounded to bf16 by the caller.
+// erf through Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. ~4 orders of magnitude below one bf16 ulp) in the
+// cancellation-free form  gelu(x) = x>0 ? x - x*q : -|x|*q,  q = 0.5 * poly(t) * exp(-x^2/2),  t = 1/(1 + p|x|/sqrt2):
+// 2 MUFU + ~12 FMA-pipe instructions instead of the ~40-instruction branchy erff() -- ncu showed the IV2 fc1 GEMM
+// epilogue issue-bound on erff (profiles/r1_gemm.md).
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(t, poly, 1.421413741f);
+    poly = fmaf(t, poly, -0.284496736f);
+    poly = fmaf(t, poly, 0.254829592f);
+    const float q = 0.5f * poly * t * fast_exp2(-z * z * 1.4426950408889634f);   // 0.5 * erfc(z)
+    const float xq = x * q;
+    return x > 0.f ? x - xq : xq;
 }
 // x * sigmoid(1.702 x) with the reference's three bf16 rounding points (HF QuickGELUActivation on
 // a bf16 tensor: mul -> sigmoid -> mul).

@@ -223,7 +223,7 @@ def decode_attention(q, k_cache, v_cache, ctx_len_dev, scale):
     kvh, max_ctx, d = k_cache.shape
     heads = q.numel() // d
     ws_bytes = lib.gvl_decode_attention_workspace(heads, d, max_ctx)
-    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=q.device)
+    ws = torch.zeros((ws_bytes // 4,), dtype=torch.float32, device=q.device)   # arrival counters must start at 0
     o = torch.empty_like(q)
     rc = lib.gvl_decode_attention(_p(q), _p(k_cache), _p(v_cache), _p(o), _p(ws), _p(ctx_len_dev), heads, kvh, d,
                                   max_ctx, float(scale), _stream())

@@ -29,7 +29,8 @@ def test_loader_is_strict_and_versioned():
     assert lib.gvl_launch_count() == 0
     # argument validation happens before any CUDA call, so it is checkable without a GPU
     assert lib.gvl_gemm_bf16(None, 0, None, 0, None, 0, 1, 8, 8, None, None, None, 0, 0, 0, 0, 0, None) == -1
-    assert lib.gvl_decode_attention_workspace(32, 96, 4096) == 32 * 16 * 98 * 4
+    # [heads][splits of 128 tokens][D+2] fp32 partials + [heads] int32 arrival counters
+    assert lib.gvl_decode_attention_workspace(32, 96, 4096) == 32 * 32 * 98 * 4 + 32 * 4
 
 
 def test_no_oracle_import_in_product():
