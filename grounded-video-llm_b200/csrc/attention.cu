@@ -275,7 +275,8 @@ int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
     static const bool force_mma = getenv("GVL_ATTN_MMA") != nullptr;   // A/B switch for bring-up / profiling
     if (!force_mma && attention_tc_supported(a)) {
         prof_begin(GVL_PROF_ATTN, 4.0 * a.batch * a.heads * (double)a.sq * a.skv * a.head_dim * (a.causal ? 0.5 : 1.0), stream);
-        int rc = attention_tc_fwd(a, stream);
+        static const bool force_v1 = getenv("GVL_ATTN_V1") != nullptr;
+        int rc = (a.sq > 128 && !force_v1) ? attention_tc2_fwd(a, stream) : attention_tc_fwd(a, stream);
         prof_end(GVL_PROF_ATTN, stream);
         return rc;
     }

@@ -413,6 +413,11 @@ int launch_tc(const AttnArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+int make_tmap_4d_attn(CUtensorMap* tm, const void* ptr, int D, int tokens, int heads, int batch, long long ts, long long hs,
+                      long long bs) {
+    return make_tmap_4d(tm, ptr, D, tokens, heads, batch, ts, hs, bs);
+}
+
 bool attention_tc_supported(const AttnArgs& a) {
     if (a.head_dim != 64 && a.head_dim != 96 && a.head_dim != 128) return false;
     if (a.o_dim % 8 != 0) return false;

@@ -1,11 +1,13 @@
-// Decode-side weight-streaming GEMV (second generation): y[M,N] = x[M,K] W[N,K]^T for M <= 4.
-// HBM-bound: the only thing that matters is bytes in flight per SM and not exposing DRAM latency more than once
-// or twice per warp. Design:
-//   * one work unit = two weight rows (SwiGLU: the gate row and the up row of one output column);
-//     grid sized so that a warp owns ~1 unit, 4 CTAs x 256 threads resident per SM;
-//   * each lane keeps U x 2 independent 128-bit streaming loads (ld.global.nc.L1::no_allocate) in flight, and the
-//     FIRST batch of weight loads is issued BEFORE the x staging / RMSNorm prologue, so the DRAM latency of the
-//     weights overlaps the prologue instead of following it;
+// Decode-side weight-streaming GEMV: y[M,N] = x[M,K] W[N,K]^T for M <= 4.
+// HBM-bound: what matters is that every SM keeps >= ~64 KB of weight loads in flight ALL the time.
+//   * one work unit = two weight rows (SwiGLU: the gate row and the up row of one output column); a warp walks its
+//     units as a flat sequence of (unit, batch) items, a batch being U x 2 independent 128-bit streaming loads
+//     (ld.global.nc.L1::no_allocate) per lane;
+//   * register double buffering: the loads of item i+1 are issued BEFORE the FMAs of item i, so the memory system
+//     never drains while a warp computes or reduces (the first-generation kernel alternated load / compute phases
+//     in lock-step across all warps and reached only ~45 % of HBM bandwidth, profiles/r1_decode.md);
+//   * the first batch is issued before the x staging / RMSNorm prologue (and before griddepcontrol.wait under PDL),
+//     so the weight stream's first DRAM round trip overlaps the prologue and the tail of the previous kernel;
 //   * x (optionally RMS-normalised with exactly the rounding of rmsnorm_bf16) lives in shared memory as bf16.
 // Reference call sites: the q_len=1 passes of Phi3DecoderLayer / LlamaDecoderLayer (modeling_phi3.py:1034-1095,
 // modeling_llama.py:699-760) and lm_head + .float() (modeling_phi3.py:1525-1526).
@@ -20,7 +22,8 @@ namespace {
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = GV_THREADS / 32;
 constexpr int GV_MAXM = 4;
-constexpr int GV_U = 4;  // 128-bit loads in flight per lane per row
+constexpr int GV_U = 4;          // 128-bit loads per lane per row per batch
+constexpr int GV_CTAS_PER_SM = 2;
 
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
@@ -44,33 +47,39 @@ __device__ __forceinline__ float dot8(uint4 w, uint4 x) {
     return s;
 }
 
+struct Batch {
+    uint4 v0[GV_U], v1[GV_U];
+};
+
 template <int MT, bool SWIGLU>
-__global__ void __launch_bounds__(GV_THREADS, 4)
-gemv2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
-             void* out, int ldo, int N, int K, const __nv_bfloat16* __restrict__ norm_w, float eps,
+__global__ void __launch_bounds__(GV_THREADS, GV_CTAS_PER_SM)
+gemv3_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw, void* out,
+             int ldo, int N, int K, const __nv_bfloat16* __restrict__ norm_w, float eps,
              const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* residual /* may alias out */, int ldr,
              int out_f32) {
     extern __shared__ __align__(16) uint8_t smem[];
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem);  // [MT][K]
     __shared__ float s_red[MT][GV_WARPS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kv = K / 8;                    // 128-bit chunks per row
+    const int kv = K / 8;                                  // 128-bit chunks per row
     const int n_units = SWIGLU ? N / 2 : (N + 1) / 2;
     const int gw = blockIdx.x * GV_WARPS + warp;
     const int nw = gridDim.x * GV_WARPS;
-    const int nb = (kv + 32 * GV_U - 1) / (32 * GV_U);   // batches per row
+    const int nb = (kv + 32 * GV_U - 1) / (32 * GV_U);     // batches per unit
+    const int my_units = gw < n_units ? (n_units - gw + nw - 1) / nw : 0;
+    const int n_items = my_units * nb;
 
     auto rows_of = [&](int unit, int& r0, int& r1) {
         if (SWIGLU) {
-            r0 = (unit / 128) * 256 + (unit % 128);      // gate row (interleaved per 256-row block, gvl/weights.py)
-            r1 = r0 + 128;                               // up row
+            r0 = (unit / 128) * 256 + (unit % 128);        // gate row (interleaved per 256-row block, gvl/weights.py)
+            r1 = r0 + 128;                                 // up row
         } else {
             r0 = unit * 2;
             r1 = (r0 + 1 < N) ? r0 + 1 : r0;
         }
     };
-    uint4 v0[GV_U], v1[GV_U];
-    auto load_batch = [&](int unit, int bidx) {
+    auto load_item = [&](int item, Batch& bt) {
+        const int unit = gw + (item / nb) * nw, bidx = item % nb;
         int r0, r1;
         rows_of(unit, r0, r1);
         const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)r0 * ldw);
@@ -78,14 +87,13 @@ gemv2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* 
 #pragma unroll
         for (int u = 0; u < GV_U; ++u) {
             const int i = (bidx * GV_U + u) * 32 + lane;
-            if (i < kv) { v0[u] = ldg_stream(w0 + i); v1[u] = ldg_stream(w1 + i); }
+            if (i < kv) { bt.v0[u] = ldg_stream(w0 + i); bt.v1[u] = ldg_stream(w1 + i); }
         }
     };
 
-    // ---- weights first: their DRAM latency overlaps the prologue below
-    bool have = false;
-    if (gw < n_units) { load_batch(gw, 0); have = true; }
-    // PDL: let the next kernel of the chain get scheduled, then wait until the producer of x has completed.
+    // ---- weights first: their DRAM latency overlaps the prologue (and, under PDL, the previous kernel's tail)
+    Batch bufA, bufB;
+    if (n_items > 0) load_item(0, bufA);
     pdl_launch_dependents();
     pdl_wait();
 
@@ -139,26 +147,27 @@ gemv2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* 
     }
     __syncthreads();
 
-    for (int unit = gw; unit < n_units; unit += nw) {
-        float a0[MT], a1[MT];
+    float a0[MT], a1[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
-        for (int bidx = 0; bidx < nb; ++bidx) {
-            if (!have) load_batch(unit, bidx);
-            have = false;
+    for (int m = 0; m < MT; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
+
+    auto consume = [&](int item, const Batch& bt) {
+        const int bidx = item % nb;
 #pragma unroll
-            for (int u = 0; u < GV_U; ++u) {
-                const int i = (bidx * GV_U + u) * 32 + lane;
-                if (i < kv) {
+        for (int u = 0; u < GV_U; ++u) {
+            const int i = (bidx * GV_U + u) * 32 + lane;
+            if (i < kv) {
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint4 xv = reinterpret_cast<const uint4*>(sx + (size_t)m * K)[i];
-                        a0[m] += dot8(v0[u], xv);
-                        a1[m] += dot8(v1[u], xv);
-                    }
+                for (int m = 0; m < MT; ++m) {
+                    const uint4 xv = reinterpret_cast<const uint4*>(sx + (size_t)m * K)[i];
+                    a0[m] += dot8(bt.v0[u], xv);
+                    a1[m] += dot8(bt.v1[u], xv);
                 }
             }
         }
+        if (bidx != nb - 1) return;
+        // ---- unit finished: reduce across the warp, fused epilogue, store
+        const int unit = gw + (item / nb) * nw;
 #pragma unroll
         for (int m = 0; m < MT; ++m) { a0[m] = wsum(a0[m]); a1[m] = wsum(a1[m]); }
         if (lane == 0) {
@@ -185,6 +194,17 @@ gemv2_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* 
                 }
             }
         }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
+    };
+
+    // ---- flat (unit, batch) item stream, register double-buffered
+    for (int item = 0; item < n_items; item += 2) {
+        if (item + 1 < n_items) load_item(item + 1, bufB);
+        consume(item, bufA);
+        if (item + 1 >= n_items) break;
+        if (item + 2 < n_items) load_item(item + 2, bufA);
+        consume(item + 1, bufB);
     }
 }
 
@@ -199,11 +219,11 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
     prof_begin(GVL_PROF_GEMV, 2.0 * (double)N * K, s);  // algorithmic bytes: the weight matrix, read once
     const int units = act == 3 ? N / 2 : (N + 1) / 2;
     int grid = (units + GV_WARPS - 1) / GV_WARPS;
-    const int cap = num_sms() * 4;
+    const int cap = num_sms() * GV_CTAS_PER_SM;
     if (grid > cap) grid = cap;
 #define GV_LAUNCH(MT, SW)                                                                                             \
     do {                                                                                                              \
-        auto kern = gemv2_kernel<MT, SW>;                                                                             \
+        auto kern = gemv3_kernel<MT, SW>;                                                                             \
         static size_t max_set = 0;                                                                                    \
         if (smem > 48 * 1024 && smem > max_set) {                                                                     \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)   \
