@@ -232,11 +232,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 auto pass1 = [&](auto mask_tag) -> float {
                     constexpr bool MASK = decltype(mask_tag)::value;
                     float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll 1
+                    // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
+                    uint32_t rr[2][32];
+                    ptx::tmem_ld_32x32(tS, rr[0]);
+#pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        uint32_t r[32];
-                        ptx::tmem_ld_32x32(tS + c * 32, r);
                         ptx::tmem_wait_ld();
+                        if (c + 1 < 4) ptx::tmem_ld_32x32(tS + (c + 1) * 32, rr[(c + 1) & 1]);
+                        const uint32_t (&r)[32] = rr[c & 1];
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
@@ -285,11 +288,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 auto pass2 = [&](auto mask_tag) -> float {
                     constexpr bool MASK = decltype(mask_tag)::value;
                     float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 1
+                    uint32_t rr[2][32];
+                    ptx::tmem_ld_32x32(tS, rr[0]);
+#pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        uint32_t r[32];
-                        ptx::tmem_ld_32x32(tS + c * 32, r);
                         ptx::tmem_wait_ld();
+                        if (c + 1 < 4) ptx::tmem_ld_32x32(tS + (c + 1) * 32, rr[(c + 1) & 1]);
+                        const uint32_t (&r)[32] = rr[c & 1];
                         uint32_t pk[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -305,6 +310,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             acc1 += p1;
                             pk[i] = pack_bf16(p0, p1);
                         }
+                        // P chunk c lands on columns [16c, 16c+16) = S columns already consumed (chunks <= c/2)
                         ptx::tmem_st_32x16(tS + c * 16, pk);
                     }
                     return acc0 + acc1;

@@ -222,7 +222,6 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
         return;
     }
     const int t1 = min(t0 + DA_CHUNK, ctx);
-    __shared__ float s_sc[DA_CHUNK];
     __shared__ float s_red[DA_THREADS / 32];
     __shared__ float s_o[DA_THREADS / 32][D];
 
@@ -243,26 +242,45 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     }
     const __nv_bfloat16* kbase = kc + (size_t)hk * max_ctx * D;
     const __nv_bfloat16* vbase = vc + (size_t)hk * max_ctx * D;
+    // ---- issue EVERY K and V load of this thread's tokens up front (one DRAM round trip instead of eight)
+    constexpr int NIT = DA_CHUNK / (DA_THREADS / 4);
+    uint4 kreg[NIT][VPL], vreg[NIT][VPL];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int t = t0 + tl + it * (DA_THREADS / 4);
+        const bool ok = t < t1;
+        const size_t off = (size_t)(ok ? t : t0) * D + sub * EPL;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) kreg[it][i] = ldg_stream(reinterpret_cast<const uint4*>(kbase + off) + i);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int t = t0 + tl + it * (DA_THREADS / 4);
+        const bool ok = t < t1;
+        const size_t off = (size_t)(ok ? t : t0) * D + sub * EPL;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) vreg[it][i] = ldg_stream(reinterpret_cast<const uint4*>(vbase + off) + i);
+    }
     // ---- pass 1: scores
     float lmax = -INFINITY;
-    for (int t = t0 + tl; t < t0 + DA_CHUNK; t += DA_THREADS / 4) {
-        float s = 0.f;
-        if (t < t1) {
-            const uint4* kp = reinterpret_cast<const uint4*>(kbase + (size_t)t * D + sub * EPL);
+    float sc[NIT];
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                uint4 v = ldg_stream(kp + i);
-                float2 f;
-                f = unpack_bf16(v.x); s += qf[i * 8 + 0] * f.x + qf[i * 8 + 1] * f.y;
-                f = unpack_bf16(v.y); s += qf[i * 8 + 2] * f.x + qf[i * 8 + 3] * f.y;
-                f = unpack_bf16(v.z); s += qf[i * 8 + 4] * f.x + qf[i * 8 + 5] * f.y;
-                f = unpack_bf16(v.w); s += qf[i * 8 + 6] * f.x + qf[i * 8 + 7] * f.y;
-            }
+    for (int it = 0; it < NIT; ++it) {
+        const int t = t0 + tl + it * (DA_THREADS / 4);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const uint4 v = kreg[it][i];
+            float2 f;
+            f = unpack_bf16(v.x); s += qf[i * 8 + 0] * f.x + qf[i * 8 + 1] * f.y;
+            f = unpack_bf16(v.y); s += qf[i * 8 + 2] * f.x + qf[i * 8 + 3] * f.y;
+            f = unpack_bf16(v.z); s += qf[i * 8 + 4] * f.x + qf[i * 8 + 5] * f.y;
+            f = unpack_bf16(v.w); s += qf[i * 8 + 6] * f.x + qf[i * 8 + 7] * f.y;
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s = (t < t1) ? s * scale : -INFINITY;
-        if (sub == 0) s_sc[t - t0] = s;
+        sc[it] = s;
         lmax = fmaxf(lmax, s);
     }
     lmax = warp_max(lmax);
@@ -276,13 +294,13 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < EPL; ++i) o[i] = 0.f;
     float lsum = 0.f;
-    for (int t = t0 + tl; t < t1; t += DA_THREADS / 4) {
-        const float p = bf16r(__expf(s_sc[t - t0] - bmax));
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const float p = bf16r(__expf(sc[it] - bmax));    // exp(-inf) = 0 for the padded tokens
         lsum += p;
-        const uint4* vp = reinterpret_cast<const uint4*>(vbase + (size_t)t * D + sub * EPL);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            uint4 v = ldg_stream(vp + i);
+            const uint4 v = vreg[it][i];
             float2 f;
             f = unpack_bf16(v.x); o[i * 8 + 0] += p * f.x; o[i * 8 + 1] += p * f.y;
             f = unpack_bf16(v.y); o[i * 8 + 2] += p * f.x; o[i * 8 + 3] += p * f.y;

@@ -253,6 +253,27 @@ def encode_images_phi(spatial, temporal, P, cfg, mode="bf16"):
     return vid.reshape(B, -1, Dm)
 
 
+def encode_images_llama(spatial, temporal, P, cfg, mode="bf16"):
+    """LLAVA_NEXT_VIDEO.encode_images, llama3 / vicuna branch (llava_next_video.py:507-518, 530-566):
+    3x3 adaptive pooling of the CLIP grid -> LlavaMultiModalProjector (linear_1, GELU, linear_2), temporal stream as for
+    phi3.5, newline = the learned `image_newline` vector. -> [B, segs*(64+16*fps+1), D]."""
+    B, segs = spatial.shape[:2]
+    frames = temporal.shape[1]
+    fps = frames // segs
+    hs = clip_hidden_states(spatial.flatten(0, 1), P["clip"], cfg["clip_heads"], cfg["clip_layers"], mode,
+                            upto=cfg["clip_layers"] - 1)
+    feat = pool_spatial_llama(hs[-1][:, 1:])                        # fp32 means of the fp32 hidden state
+    sp = mlp2(feat, P["mm.linear_1.weight"], P["mm.linear_1.bias"], P["mm.linear_2.weight"], P["mm.linear_2.bias"], mode)
+    tp = temporal.reshape(B, segs, fps, *temporal.shape[2:]).permute(0, 1, 3, 2, 4, 5).flatten(0, 1)
+    xv = iv2_forward(tp, P["iv2"], cfg["iv2_heads"], cfg["iv2_depth"], mode)
+    pooled = _r(pool_temporal(xv, fps), mode)
+    tm = mlp2(pooled, P["vp.up_proj.weight"], P["vp.up_proj.bias"], P["vp.down_proj.weight"], P["vp.down_proj.bias"], mode)
+    Dm = sp.shape[-1]
+    nl = _r(P["image_newline"].float(), mode).reshape(1, 1, 1, Dm).expand(B, segs, 1, Dm)
+    vid = torch.cat([sp.reshape(B, segs, -1, Dm), tm.reshape(B, segs, -1, Dm), nl], dim=2)
+    return vid.reshape(B, -1, Dm)
+
+
 def splice_embeds(ids, embed_table, visual, vis_last=False):
     """prepare_multimodal_inputs for one sample (llava_next_video.py:568-596)."""
     pos = int((ids == IMAGE_TOKEN_INDEX).nonzero()[0])

@@ -221,7 +221,23 @@ def gold_index_maps():
     mine2 = torch.cat([sp, tm, nlr], dim=2).reshape(B, -1, 8)
     assert vid.shape == (B, segs * (156 + 16 * fps + 1), 8), vid.shape
     assert torch.equal(vid, mine2), "encode_images ordering oracle != reference"
-    _save("encode_images_order.npz", video_features=vid.numpy(), segs=np.int64(segs), fps=np.int64(fps))
+    # llama3 / vicuna branch of the same method (3x3 pooled CLIP grid, learned image_newline)
+    me4 = _Self()
+    me4.llm = "llama3"
+    me4.vision_tower = Tower()
+    me4.video_encoder = Video()
+    me4.multi_modal_projector = lambda t: t[..., :8]
+    me4.video_projecter = lambda t: t
+    me4.image_newline = -(torch.arange(8).double() + 7000)
+    me4.config = type("C", (), {"hidden_size": 8})()
+    vid_l = enc(me4, samples)
+    sp_l = O.pool_spatial_llama(feat2)[..., :8].reshape(B, segs, 64, 8)
+    nl_l = me4.image_newline.reshape(1, 1, 1, 8).expand(B, segs, 1, 8)
+    mine_l = torch.cat([sp_l, tm, nl_l], dim=2).reshape(B, -1, 8)
+    assert vid_l.shape == (B, segs * (64 + 16 * fps + 1), 8), vid_l.shape
+    assert torch.allclose(vid_l, mine_l, rtol=0, atol=1e-9), "encode_images (llama) ordering oracle != reference"
+    _save("encode_images_order.npz", video_features=vid.numpy(), video_features_llama=vid_l.numpy(),
+          segs=np.int64(segs), fps=np.int64(fps))
 
     # prepare_multimodal_inputs
     prep = R.extract(f, "prepare_multimodal_inputs", "LLAVA_NEXT_VIDEO", ns)

@@ -318,3 +318,34 @@ def test_pipeline_small_end_to_end(gvl):
     top2 = torch.topk(lg_ref[0], 2).values
     if float(top2[0] - top2[1]) > 5e-2:
         assert int(toks[0]) == toks_ref[0]
+
+
+def test_pipeline_small_llama_variant(gvl):
+    """Llama-3 / LLaVA-Next branch (BASELINE config 4 shapes per segment: 64 + 128 + 1 = 193 visual tokens, GQA decoder,
+    plain RoPE with the reference's bf16-autocast matmul quirk) on a reduced-depth model, vs the oracle."""
+    from gvl import synth
+    lm = dict(synth.LLAMA3_8B, layers=2, vocab=1000 + 302, dim=256, heads=4, kv_heads=2, head_dim=64, ffn=512)
+    params, lm_cfg, clip_cfg, iv2_cfg = synth.make_params("llama3", device="cpu", seed=4, lm=lm, clip=dict(synth.CLIP_L336, layers=2),
+                                                          iv2=dict(synth.IV2_1B, depth=3, gamma=0.1), lm_dtype=torch.float32)
+    m = gvl.model.LLAVA_NEXT_VIDEO(params, llm="llama3", num_frames=8, num_segs=1, lm_cfg=lm_cfg, clip_cfg=clip_cfg,
+                                   iv2_cfg=iv2_cfg, max_ctx=512)
+    g = torch.Generator().manual_seed(99)
+    sp, tp = torch.randn(1, 1, 3, 336, 336, generator=g), torch.randn(1, 8, 3, 224, 224, generator=g)
+    ids = torch.randint(3, 1000, (20,), generator=torch.Generator().manual_seed(3))
+    ids[5] = -200
+    samples = {"spatial_pixel_values": sp, "temporal_pixel_values": tp, "input_ids": [ids.tolist()]}
+    feats = m.encode_images(samples)
+    assert feats.shape == (1, 193, 256)
+    OP = {"clip": params["vision_tower"], "iv2": params["video_encoder"], "image_newline": params["image_newline"]}
+    OP.update({"mm." + k: v for k, v in params["multi_modal_projector"].items()})
+    OP.update({"vp." + k: v for k, v in params["video_projecter"].items()})
+    ref = O.encode_images_llama(sp, tp, OP, dict(clip_heads=16, clip_layers=2, iv2_heads=16, iv2_depth=3), mode="bf16")
+    _cmp(feats, ref, atol=0.03, rtol=0.03)
+    table = O.bf(params["language_model"]["model.embed_tokens.weight"].float())
+    emb = O.splice_embeds(ids, table, ref[0])
+    lcfg = dict(arch="llama", layers=2, heads=4, kv_heads=2, head_dim=64, eps=1e-5, rope=dict(type="plain", base=500000.0, bf16_quirk=True))
+    ref_logits = O.lm_forward(emb, params["language_model"], lcfg, mode="bf16")
+    logits = m.language_model(inputs_embeds=emb.cuda()[None]).logits[0]
+    _cmp(logits, ref_logits, atol=_logit_tol(ref_logits))
+    toks = m.generate(samples, max_new_tokens=3)[0]
+    assert toks.shape == (3,)
