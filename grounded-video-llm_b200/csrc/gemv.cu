@@ -216,10 +216,10 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
     if (M < 1 || M > GV_MAXM || K % 256 != 0 || (act != 0 && act != 3)) return GVL_ERR_ARG;
     if (act == 3 && N % 256 != 0) return GVL_ERR_ARG;
     {
-        // default: the shared-memory-staged cp.async.bulk kernel (gemv_bulk.cu); GVL_GEMV_BULK=0 selects this file's
-        // register-staged kernel (kept for A/B measurements)
+        // GVL_GEMV_BULK=1 selects the shared-memory-staged cp.async.bulk kernel (gemv_bulk.cu); it measured SLOWER
+        // than this file's register-staged kernel in round 1 (profiles/r1_decode.md) and is kept for A/B work only.
         static const char* env = getenv("GVL_GEMV_BULK");
-        if (!(env && env[0] == '0'))
+        if (env && env[0] == '1')
             return gemv_bulk_bf16(x, ldx, W, ldw, out, ldo, M, N, K, norm_w, eps, bias, residual, ldr, act, out_f32, s);
     }
     const size_t smem = (size_t)M * K * 2;
