@@ -29,6 +29,8 @@ def _sources():
 def _digest():
     h = hashlib.sha256()
     for f in sorted(os.listdir(CSRC)):
+        if not os.path.isfile(os.path.join(CSRC, f)):
+            continue
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())

@@ -9,7 +9,9 @@
 // lives in device memory so the graph is replayed without host round trips.
 #include <vector>
 #include "gvl_internal.h"
+#include <stdlib.h>
 #include "decode.h"
+#include "decode_mega.h"
 #include "../../include/gvl.h"
 
 using namespace gvl;
@@ -39,6 +41,10 @@ struct gvl_lm {
     long long g_eos = 0, g_pad = 0;
     bool use_graph = true;
     bool use_pdl = true;
+    // single-kernel decode step (decode_mega.cu); GVL_DECODE_MEGA=0 falls back to the per-op kernel chain
+    bool use_mega = true;
+    MegaPlan* plan_dev = nullptr;
+    unsigned* grid_bar = nullptr;
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
     __nv_bfloat16* kcache(int l) const { return kv + (size_t)l * kv_layer_elems(); }
@@ -113,6 +119,8 @@ int enqueue_decode_step_impl(gvl_lm* lm, long long* tokens_out, float* logits_ou
 // PDL is enabled for the decode chain only (every kernel in it starts with pdl_wait()).
 int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
                         cudaStream_t s) {
+    if (lm->use_mega && lm->plan_dev)
+        return decode_mega_launch(lm->plan_dev, lm->grid_bar, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = lm->use_pdl;
     const int rc = enqueue_decode_step_impl(lm, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = false;
@@ -149,6 +157,54 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
         cudaEventCreateWithFlags(&lm->ev_out, cudaEventDisableTiming) != cudaSuccess) { rc = GVL_ERR_CUDA; goto fail; }
     cudaMemset(lm->st, 0, sizeof(DecodeState));
     cudaMemset(lm->da_ws, 0, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx));
+    {
+        const char* env = getenv("GVL_DECODE_MEGA");
+        lm->use_mega = !(env && env[0] == '0') && w->n_layers <= MEGA_MAX_LAYERS && w->dim <= 14336 && w->ffn <= 14336 &&
+                       (w->heads * w->head_dim) <= 14336 && w->dim % 8 == 0 && w->ffn % 128 == 0 &&
+                       (w->head_dim == 64 || w->head_dim == 96 || w->head_dim == 128);
+        if (lm->use_mega) {
+            MegaPlan* hp = new MegaPlan();
+            hp->n_layers = w->n_layers; hp->dim = w->dim; hp->heads = w->heads; hp->kv_heads = w->kv_heads;
+            hp->head_dim = w->head_dim; hp->vocab = w->vocab; hp->max_ctx = w->max_ctx;
+            hp->scale = 1.0f / sqrtf((float)w->head_dim);
+            auto mk = [&](const void* W, int N, int K, const __nv_bfloat16* x, const void* norm_w, const void* bias,
+                          const __nv_bfloat16* residual, void* out, int act, int out_f32) {
+                MegaOp op;
+                op.W = (const __nv_bfloat16*)W; op.ldw = K; op.K = K;
+                op.nseg = (K + 4095) / 4096;
+                while (K % (op.nseg * 8) != 0) ++op.nseg;      // K % 8 == 0 is checked above: terminates
+                op.seg_len = K / op.nseg;
+                op.units = act == 3 ? N / 2 : N;
+                op.act = act; op.out_f32 = out_f32; op.x = x; op.norm_w = (const __nv_bfloat16*)norm_w; op.eps = w->rms_eps;
+                op.bias = (const __nv_bfloat16*)bias; op.residual = residual; op.out = out;
+                return op;
+            };
+            const int HD = w->heads * w->head_dim;
+            for (int l = 0; l < w->n_layers; ++l) {
+                const gvl_lm_layer& L = lm->layers[l];
+                hp->ops[l * 4 + 0] = mk(L.qkv_w, qkv_n, D, lm->dx, L.in_norm_w, nullptr, nullptr, lm->dqkv, 0, 0);
+                hp->ops[l * 4 + 1] = mk(L.o_w, D, HD, lm->dattn, nullptr, nullptr, lm->dx, lm->dx, 0, 0);
+                hp->ops[l * 4 + 2] = mk(L.gate_up_w, 2 * w->ffn, D, lm->dx, L.post_norm_w, nullptr, nullptr, lm->dmid, 3, 0);
+                hp->ops[l * 4 + 3] = mk(L.down_w, D, w->ffn, lm->dmid, nullptr, nullptr, lm->dx, lm->dx, 0, 0);
+            }
+            hp->ops[w->n_layers * 4] = mk(w->lm_head_w, w->vocab, D, lm->dx, w->final_norm_w, w->lm_head_b, nullptr, lm->dlogits, 0, 1);
+            hp->embed = (const __nv_bfloat16*)w->embed;
+            hp->rope_cos = (const __nv_bfloat16*)w->rope_cos; hp->rope_sin = (const __nv_bfloat16*)w->rope_sin;
+            hp->kv = lm->kv; hp->x = lm->dx; hp->qkv = lm->dqkv; hp->attn_out = lm->dattn; hp->mid = lm->dmid;
+            hp->logits = lm->dlogits;
+            hp->att_ws = lm->da_ws;
+            const int nsplit = (w->max_ctx + 127) / 128;
+            hp->att_counters = reinterpret_cast<int*>(lm->da_ws + (size_t)w->heads * nsplit * (w->head_dim + 2));
+            hp->st = lm->st;
+            bool ok = dev_alloc(&lm->grid_bar, 1) == GVL_OK && dev_alloc(&lm->plan_dev, 1) == GVL_OK;
+            if (ok) {
+                hp->grid_bar = lm->grid_bar;
+                ok = cudaMemcpy(lm->plan_dev, hp, sizeof(MegaPlan), cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+            delete hp;
+            if (!ok) { rc = GVL_ERR_NOMEM; goto fail; }
+        }
+    }
     *out = lm;
     return GVL_OK;
 fail:
@@ -163,7 +219,7 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->x); cudaFree(lm->h); cudaFree(lm->qkv); cudaFree(lm->q); cudaFree(lm->attn); cudaFree(lm->mid);
     cudaFree(lm->dx); cudaFree(lm->dqkv); cudaFree(lm->dq); cudaFree(lm->dattn); cudaFree(lm->dmid);
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
-    cudaFree(lm->tok_buf); cudaFree(lm->logit_buf);
+    cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar);
     if (lm->cs) cudaStreamDestroy(lm->cs);
     if (lm->ev_in) cudaEventDestroy(lm->ev_in);
     if (lm->ev_out) cudaEventDestroy(lm->ev_out);
@@ -269,7 +325,7 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
             if (e != cudaSuccess) return GVL_ERR_CUDA;
             lm->g_logits = lbuf; lm->g_eos = eos_id; lm->g_pad = pad_id;
         }
-        const long long per_step = 2 + (long long)lm->w.n_layers * 6 + 2;
+        const long long per_step = (lm->use_mega && lm->plan_dev) ? 1 : 2 + (long long)lm->w.n_layers * 6 + 2;
         for (int i = 0; i < n_steps; ++i) {
             CU(cudaGraphLaunch(lm->graph, s));
             g_launch_count += per_step;
