@@ -83,6 +83,14 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
+// optional per-CTA phase trace (clock64 at: x staged / work done / barrier passed), MegaPlan::trace != nullptr
+struct Tracer {
+    long long* p;
+    __device__ __forceinline__ void mark(int tid) {
+        if (p != nullptr && tid == 0) *p++ = clock64();
+    }
+};
+
 __device__ __forceinline__ int units_of(int gl, int n_units, int TW) { return gl < n_units ? (n_units - gl + TW - 1) / TW : 0; }
 __device__ __forceinline__ int row_of(const MegaOp& op, int unit, int sel) {
     return op.act == 3 ? (unit / 128) * 256 + (unit % 128) + sel * 128 : unit;
@@ -95,7 +103,8 @@ struct RingState {
 };
 
 __device__ __forceinline__ void gemv_phase(const MegaOp& op_g, __nv_bfloat16* sx, uint8_t* ring, uint64_t* s_full,
-                                           uint64_t* s_empty, float* s_red, RingState& rs, int tid, int warp, int lane) {
+                                           uint64_t* s_empty, float* s_red, RingState& rs, int tid, int warp, int lane,
+                                           Tracer& tr) {
     const MegaOp op = op_g;      // registers: the plan lives in global memory and the stores below could alias it
     const int K = op.K, kv = K / 8;
     // ---- stage x (global, written by other CTAs in the previous phase -> L1-bypassing loads), optional RMSNorm
@@ -131,6 +140,7 @@ __device__ __forceinline__ void gemv_phase(const MegaOp& op_g, __nv_bfloat16* sx
         }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    tr.mark(tid);
 
     const int TW = gridDim.x * MG_CONSUMERS;
     const int nsel = op.act == 3 ? 2 : 1;
@@ -421,29 +431,32 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, long long* tokens_out, f
     }
     // ---------------------------------------------------------------- consumers
     unsigned epoch = 0;
+    Tracer tr{P.trace ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE : nullptr};
+    tr.mark(tid);
     // embed the current token into the residual stream (CTA 0), everyone waits
     if (blockIdx.x == 0) {
         const long long tok = P.st->cur_token;
         const uint4* src = reinterpret_cast<const uint4*>(P.embed + (size_t)tok * P.dim);
         for (int i = tid; i < P.dim / 8; i += 256) reinterpret_cast<uint4*>(P.x)[i] = src[i];
     }
-    grid_barrier(P.grid_bar, epoch, tid);
+    tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
     for (int l = 0; l < P.n_layers; ++l) {
-        gemv_phase(P.ops[l * 4 + 0], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane);     // norm + qkv
-        grid_barrier(P.grid_bar, epoch, tid);
+        gemv_phase(P.ops[l * 4 + 0], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // norm + qkv
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
         if (P.head_dim == 96) attention_phase<96>(P, l, s_att[warp], warp, lane);
         else if (P.head_dim == 128) attention_phase<128>(P, l, s_att[warp], warp, lane);
         else attention_phase<64>(P, l, s_att[warp], warp, lane);
-        grid_barrier(P.grid_bar, epoch, tid);
-        gemv_phase(P.ops[l * 4 + 1], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane);     // o_proj + residual
-        grid_barrier(P.grid_bar, epoch, tid);
-        gemv_phase(P.ops[l * 4 + 2], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane);     // norm + gate_up + SwiGLU
-        grid_barrier(P.grid_bar, epoch, tid);
-        gemv_phase(P.ops[l * 4 + 3], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane);     // down + residual
-        grid_barrier(P.grid_bar, epoch, tid);
+        tr.mark(tid);                                   // keeps 3 marks per phase (no staging step here)
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
+        gemv_phase(P.ops[l * 4 + 1], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // o_proj + residual
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
+        gemv_phase(P.ops[l * 4 + 2], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // norm + gate_up + SwiGLU
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
+        gemv_phase(P.ops[l * 4 + 3], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // down + residual
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
     }
-    gemv_phase(P.ops[P.n_layers * 4], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane);    // norm + lm_head + bias
-    grid_barrier(P.grid_bar, epoch, tid);
+    gemv_phase(P.ops[P.n_layers * 4], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);    // norm + lm_head + bias
+    tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
     // ---- greedy pick + bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
     if (blockIdx.x == 0) {
         __shared__ float sv_[MG_CONSUMERS];

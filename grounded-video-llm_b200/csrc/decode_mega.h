@@ -19,6 +19,7 @@ struct MegaOp {                 // one weight-streaming GEMV phase (M = 1)
 };
 
 constexpr int MEGA_MAX_LAYERS = 48;
+constexpr int MEGA_TRACE_STRIDE = 768;   // clock64 marks per CTA per step: 1 + 15 * layers + 3
 
 struct MegaPlan {
     int n_layers, dim, heads, kv_heads, head_dim, vocab, max_ctx;
@@ -33,6 +34,7 @@ struct MegaPlan {
     int* att_counters;          // [heads], zero between launches
     unsigned* grid_bar;
     DecodeState* st;
+    long long* trace;           // optional [gridDim.x][MEGA_TRACE_STRIDE] phase timestamps of the LAST step (bring-up / profiling)
 };
 
 size_t decode_mega_smem();

@@ -45,6 +45,7 @@ struct gvl_lm {
     bool use_mega = true;
     MegaPlan* plan_dev = nullptr;
     unsigned* grid_bar = nullptr;
+    long long* trace = nullptr;       // GVL_MEGA_TRACE=1: per-CTA phase timestamps of the last decode step
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
     __nv_bfloat16* kcache(int l) const { return kv + (size_t)l * kv_layer_elems(); }
@@ -196,6 +197,11 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
             const int nsplit = (w->max_ctx + 127) / 128;
             hp->att_counters = reinterpret_cast<int*>(lm->da_ws + (size_t)w->heads * nsplit * (w->head_dim + 2));
             hp->st = lm->st;
+            hp->trace = nullptr;
+            if (getenv("GVL_MEGA_TRACE") && dev_alloc(&lm->trace, (size_t)num_sms() * MEGA_TRACE_STRIDE) == GVL_OK) {
+                cudaMemset(lm->trace, 0, (size_t)num_sms() * MEGA_TRACE_STRIDE * sizeof(long long));
+                hp->trace = lm->trace;
+            }
             bool ok = dev_alloc(&lm->grid_bar, 1) == GVL_OK && dev_alloc(&lm->plan_dev, 1) == GVL_OK;
             if (ok) {
                 hp->grid_bar = lm->grid_bar;
@@ -219,7 +225,7 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->x); cudaFree(lm->h); cudaFree(lm->qkv); cudaFree(lm->q); cudaFree(lm->attn); cudaFree(lm->mid);
     cudaFree(lm->dx); cudaFree(lm->dqkv); cudaFree(lm->dq); cudaFree(lm->dattn); cudaFree(lm->dmid);
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
-    cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar);
+    cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar); cudaFree(lm->trace);
     if (lm->cs) cudaStreamDestroy(lm->cs);
     if (lm->ev_in) cudaEventDestroy(lm->ev_in);
     if (lm->ev_out) cudaEventDestroy(lm->ev_out);
@@ -335,6 +341,16 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
     if (want_logits) CU(cudaMemcpyAsync(logits_out, lbuf, (size_t)n_steps * lm->w.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(cudaEventRecord(lm->ev_out, s));
     CU(cudaStreamWaitEvent(caller, lm->ev_out, 0));
+    return GVL_OK;
+}
+
+int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas, int* stride) {
+    if (!lm || !host_out || !lm->trace) return GVL_ERR_STATE;
+    const int n = num_sms() < max_ctas ? num_sms() : max_ctas;
+    if (cudaDeviceSynchronize() != cudaSuccess) return GVL_ERR_CUDA;
+    CU(cudaMemcpy(host_out, lm->trace, (size_t)n * MEGA_TRACE_STRIDE * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (n_ctas) *n_ctas = n;
+    if (stride) *stride = MEGA_TRACE_STRIDE;
     return GVL_OK;
 }
 

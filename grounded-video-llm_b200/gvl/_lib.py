@@ -102,6 +102,7 @@ _SIGS = {
     "gvl_lm_decode": (c_i, [c_vp, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_first_token": (c_vp, [c_vp]),
     "gvl_lm_set_graph": (c_i, [c_vp, c_i]),
+    "gvl_lm_mega_trace": (c_i, [c_vp, c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
     "gvl_profile_enable": (c_i, [c_i]),
     "gvl_profile_collect": (c_i, [c_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(c_ll)]),

@@ -215,6 +215,11 @@ int gvl_lm_set_graph(gvl_lm* lm, int on);
 int gvl_profile_enable(int on);
 int gvl_profile_collect(int kind, double* total_ms, double* total_work, long long* launches);
 
+/* Bring-up / profiling: with GVL_MEGA_TRACE=1 in the environment at gvl_lm_create time the single-kernel decode step
+ * records clock64() per CTA at every phase boundary of the LAST step; this copies [n_ctas][stride] int64 marks to the
+ * host (synchronises the device). Returns GVL_ERR_STATE when tracing is off.                                          */
+int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas, int* stride);
+
 /* first generated token (argmax of the prefill logits), device int64 */
 const long long* gvl_lm_first_token(gvl_lm* lm);
 
