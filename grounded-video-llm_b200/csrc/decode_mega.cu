@@ -1,12 +1,30 @@
 // One persistent kernel per decode step ("megakernel"): the 4 x L + 1 weight matrices of a step are streamed
 // through a shared-memory ring by ONE producer warp per SM that never stops for phase boundaries (weights do not
 // depend on activations), while 8 consumer warps per SM walk the phases of the step
-//     embed | per layer: [norm+qkv] B [rope + KV append + split-KV attention + combine] B [o_proj+res] B
-//           [norm+gate_up+SwiGLU] B [down+res] B | [norm+lm_head+bias] B argmax/bookkeeping
-// separated by grid-wide barriers B (atomic counter, all 148 CTAs co-resident, cooperative launch).
-// While the consumers sit in a barrier the ring keeps filling (~190 KB per SM, ~4 us of HBM time chip-wide), so the
-// HBM stream does not drain at kernel/phase boundaries -- the ~5 us fixed cost per GEMV launch measured for the
-// per-op kernels (profiles/r1_decode.md) disappears.
+//     per layer: [norm+qkv] B [rope + KV append + split-KV attention] B [merge + o_proj+res] B
+//                [norm+gate_up+SwiGLU] B [down+res] B | [norm+lm_head+bias+argmax] B bookkeeping
+// separated by grid-wide barriers B (atomic counter, all CTAs co-resident, cooperative launch). One launch runs ALL
+// the steps of a gvl_lm_decode call (token, position and EOS state live in device memory).
+//
+// GEMV phases: a work item is 8 weight rows x <=512 k (8 KB). The decode path owns a PACKED copy of the weights
+// (decode_mega_pack: item-major, inside an item [32-k chunk][row][32 k]) so that one item is ONE contiguous 8 KB
+// cp.async.bulk into a consumer warp's ring slot -- tools/probe_stream.cu measured 4.8 TB/s with 1 KB row-wise copies
+// and 7.2 TB/s with >= 4 KB copies on B200 -- and the interleave makes the fragment loads bank-conflict free without
+// padding. The warp multiplies the item with mma.sync.m16n8k16 (A = the activation vector broadcast over the
+// 16 rows, B = the 8 weight rows; k is permuted identically on both operands so every lane feeds its fragments with
+// 128-bit shared-memory loads). That is ~6 warp instructions per KB of weights, so the consumers drain the ring several
+// times faster than HBM fills it: the ring runs near-empty inside a phase and absorbs ~4 us of HBM stream while the
+// consumers sit in a barrier / stage the next activation vector. Items of a CTA are dealt round-robin to its 8 warps
+// (k-split inside the CTA, partial sums reduced through shared memory in a fixed order -> deterministic).
+// Every consumer warp has its own 3-slot ring fed by one lane of the producer warp, which keeps at most `inflight`
+// copies per lane outstanding: 8 x 8 KB x 148 SMs = 9.5 MB in flight is enough for the full HBM rate, while deeper
+// queues (the first version had 28 MB outstanding) only add queueing delay (4+ us measured) to every latency-critical
+// load of the phase boundaries (activation staging, barrier atomics, q/k of the attention phase).
+//
+// Attention phase: the flat (head, token) space is cut into equal contiguous ranges, one per consumer warp of the
+// grid; a warp streams K/V rows (4 lanes per token, 8 tokens per pass, 4 passes of K and V loads in flight) with an
+// online softmax, warps of a CTA merge through shared memory, and the <= G/H + 2 CTA partials per head are merged by
+// every CTA while it stages the o_proj input (no atomics, no extra barrier).
 //
 // Reference semantics per phase: Phi3DecoderLayer / LlamaDecoderLayer with q_len = 1 (modeling_phi3.py:1034-1095,
 // 629-775, 413-445; modeling_llama.py:699-760), lm_head + .float() (modeling_phi3.py:1525-1526), greedy pick of
@@ -15,6 +33,7 @@
 #include "ptx.cuh"
 #include "decode.h"
 #include "decode_mega.h"
+#include <stdlib.h>
 
 namespace gvl {
 
@@ -22,36 +41,45 @@ namespace {
 
 constexpr int MG_CONSUMERS = 8;
 constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 1);
-constexpr int MG_SLOT_BYTES = 8192;                       // one segment (<= 4096 bf16)
-constexpr int MG_STAGE_BYTES = MG_CONSUMERS * MG_SLOT_BYTES;
-constexpr int MG_STAGES = 3;
-constexpr int MG_XMAX = 14336;                            // largest K staged (elements; Llama-3-8B ffn)
-constexpr int MG_SMEM = MG_STAGES * MG_STAGE_BYTES + MG_XMAX * 2 + 1024;
-constexpr int MG_SPLIT = 128;                             // context tokens per attention task
+constexpr int MG_SLOT_BYTES = MEGA_ROWS * MEGA_SEG * 2;          // 8192: one packed item
+constexpr int MG_SLOTS = 3;                                      // ring depth per consumer warp
+constexpr int MG_RING_BYTES = MG_CONSUMERS * MG_SLOTS * MG_SLOT_BYTES;   // 196608
+constexpr int MG_SMEM_LIMIT = 232448 - 2048;                     // 227 KB opt-in minus static shared memory
+constexpr int MG_ATT_SHORT = 128;                                // ctx <= this: one warp per head
 
-__device__ __forceinline__ float wsum_m(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+__host__ __device__ inline int att_warp_len(int ctx, int H, int G) {
+    if (ctx <= MG_ATT_SHORT) return ctx;
+    const int TW = G * MG_CONSUMERS;
+    const int per = (H * ctx + TW - 1) / TW;
+    return (per + 7) & ~7;
 }
-__device__ __forceinline__ float dot8m(uint4 w, uint4 x) {
-    float2 a, b;
-    float s;
-    a = unpack_bf16(w.x); b = unpack_bf16(x.x); s = a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.y); b = unpack_bf16(x.y); s += a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.z); b = unpack_bf16(x.z); s += a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.w); b = unpack_bf16(x.w); s += a.x * b.x + a.y * b.y;
-    return s;
-}
+__host__ __device__ inline int att_scratch_bytes(int D) { return MG_CONSUMERS * 2 * D * 4 + 2 * MG_CONSUMERS * (D + 4) * 4; }
+
 __device__ __forceinline__ void bulk_g2s_m(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ uint4 ldg_stream4(const uint4* p) {
@@ -61,13 +89,26 @@ __device__ __forceinline__ uint4 ldg_stream4(const uint4* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 consumer threads
 
-// consumers-only grid barrier (named barrier 1 = the 256 consumer threads of this CTA)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid) {
-    __threadfence();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+// consumers-only grid barrier
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid, int ablate = 0) {
+    cbar();
+    if (ablate & 1) return;                          // timing ablation only (results are wrong)
     ++epoch;
     if (tid == 0) {
+        __threadfence();
         atomicAdd(counter, 1u);
         const unsigned target = epoch * gridDim.x;
         if (ld_acquire_u32(counter) < target) {
@@ -80,7 +121,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
             }
         }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    cbar();
 }
 
 // optional per-CTA phase trace (clock64 at: x staged / work done / barrier passed), MegaPlan::trace != nullptr
@@ -91,432 +132,768 @@ struct Tracer {
     }
 };
 
-__device__ __forceinline__ int units_of(int gl, int n_units, int TW) { return gl < n_units ? (n_units - gl + TW - 1) / TW : 0; }
-__device__ __forceinline__ int row_of(const MegaOp& op, int unit, int sel) {
-    return op.act == 3 ? (unit / 128) * 256 + (unit % 128) + sel * 128 : unit;
+__device__ __forceinline__ int row_base_of(const MegaOp& op, int unit, int sel) {
+    const int o = unit * MEGA_ROWS;
+    return op.act == 3 ? (o / 128) * 256 + (o % 128) + sel * 128 : o;
 }
 
-// ------------------------------------------------------------------ consumer side of one GEMV phase
-struct RingState {
-    int stage;
-    uint32_t phase;
+struct Smem {
+    uint8_t* ring;      // [warp][slot][8 KB]
+    uint8_t* xa;        // activation staging area / attention scratch
+    float* part;        // per-item partial sums (8 floats per item)
+    uint64_t* full;     // [warp][slot]
+    uint64_t* empty;    // [warp][slot]
+    float* red;
+    float* rope;        // [2][128]: cos / sin row of the current position
 };
 
-__device__ __forceinline__ void gemv_phase(const MegaOp& op_g, __nv_bfloat16* sx, uint8_t* ring, uint64_t* s_full,
-                                           uint64_t* s_empty, float* s_red, RingState& rs, int tid, int warp, int lane,
-                                           Tracer& tr) {
-    const MegaOp op = op_g;      // registers: the plan lives in global memory and the stores below could alias it
-    const int K = op.K, kv = K / 8;
-    // ---- stage x (global, written by other CTAs in the previous phase -> L1-bypassing loads), optional RMSNorm
-    float ss = 0.f;
-    for (int i = tid; i < kv; i += 256) {
-        const uint4 v = ldcg4(op.x + (size_t)i * 8);
-        reinterpret_cast<uint4*>(sx)[i] = v;
-        if (op.norm_w) {
-            float2 f;
-            f = unpack_bf16(v.x); ss += f.x * f.x + f.y * f.y;
-            f = unpack_bf16(v.y); ss += f.x * f.x + f.y * f.y;
-            f = unpack_bf16(v.z); ss += f.x * f.x + f.y * f.y;
-            f = unpack_bf16(v.w); ss += f.x * f.x + f.y * f.y;
-        }
+struct NormPre {        // RMSNorm weights of the NEXT phase, loaded before the grid barrier (K <= 4096)
+    uint4 v[2];
+};
+__device__ __forceinline__ void prefetch_norm(const MegaOp& op, NormPre& np, int tid) {
+    if (op.norm_w == nullptr || op.K > 4096) return;
+    const int kv = op.K / 8;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (tid + u * 256 < kv) np.v[u] = __ldg(reinterpret_cast<const uint4*>(op.norm_w) + tid + u * 256);
+}
+
+__device__ __forceinline__ uint4 norm8(uint4 v, uint4 wv, float rstd) {
+    uint4 o;
+    float2 f, g;
+    f = unpack_bf16(v.x); g = unpack_bf16(wv.x); o.x = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+    f = unpack_bf16(v.y); g = unpack_bf16(wv.y); o.y = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+    f = unpack_bf16(v.z); g = unpack_bf16(wv.z); o.z = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+    f = unpack_bf16(v.w); g = unpack_bf16(wv.w); o.w = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+    return o;
+}
+__device__ __forceinline__ float sumsq8(uint4 v) {
+    float2 f;
+    float ss;
+    f = unpack_bf16(v.x); ss = f.x * f.x + f.y * f.y;
+    f = unpack_bf16(v.y); ss += f.x * f.x + f.y * f.y;
+    f = unpack_bf16(v.z); ss += f.x * f.x + f.y * f.y;
+    f = unpack_bf16(v.w); ss += f.x * f.x + f.y * f.y;
+    return ss;
+}
+
+// ------------------------------------------------------------------ x staging: vector in global memory (+ RMSNorm)
+__device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat16* xsrc, const NormPre& np, const Smem& S,
+                                            int tid, int warp, int lane) {
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
+    const int kv = op.K / 8;
+    if (op.norm_w == nullptr) {
+        for (int i = tid; i < kv; i += 256) reinterpret_cast<uint4*>(sx)[i] = ldcg4(xsrc + (size_t)i * 8);
+        cbar();
+        return;
     }
-    if (op.norm_w) {
-        ss = wsum_m(ss);
-        if (lane == 0) s_red[warp] = ss;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (op.K <= 4096) {
+        // one round trip: x stays in registers across the block reduction, norm weights were prefetched
+        uint4 xv[2];
+        float ss = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < kv) xv[u] = ldcg4(xsrc + (size_t)(tid + u * 256) * 8);   // written by other CTAs: L1-bypassing
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < kv) ss += sumsq8(xv[u]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) S.red[warp] = ss;
+        cbar();
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < MG_CONSUMERS; ++w) t += s_red[w];
-        const float rstd = rsqrtf(t / K + op.eps);
-        for (int i = tid; i < kv; i += 256) {
-            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(op.norm_w) + i);
-            uint4 v = reinterpret_cast<uint4*>(sx)[i], o;
-            float2 f, g;
-            f = unpack_bf16(v.x); g = unpack_bf16(wv.x); o.x = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            f = unpack_bf16(v.y); g = unpack_bf16(wv.y); o.y = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            f = unpack_bf16(v.z); g = unpack_bf16(wv.z); o.z = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            f = unpack_bf16(v.w); g = unpack_bf16(wv.w); o.w = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            reinterpret_cast<uint4*>(sx)[i] = o;
-        }
+        for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
+        const float rstd = rsqrtf(t / op.K + op.eps);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < kv) reinterpret_cast<uint4*>(sx)[tid + u * 256] = norm8(xv[u], np.v[u], rstd);
+        cbar();
+        return;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    tr.mark(tid);
+    float ss = 0.f;
+    for (int i = tid; i < kv; i += 256) {
+        const uint4 v = ldcg4(xsrc + (size_t)i * 8);
+        reinterpret_cast<uint4*>(sx)[i] = v;
+        ss += sumsq8(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) S.red[warp] = ss;
+    cbar();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
+    const float rstd = rsqrtf(t / op.K + op.eps);
+    for (int i = tid; i < kv; i += 256)
+        reinterpret_cast<uint4*>(sx)[i] = norm8(reinterpret_cast<uint4*>(sx)[i], __ldg(reinterpret_cast<const uint4*>(op.norm_w) + i), rstd);
+    cbar();
+}
 
-    const int TW = gridDim.x * MG_CONSUMERS;
-    const int nsel = op.act == 3 ? 2 : 1;
-    const int ipu = nsel * op.nseg;
-    const int gl = blockIdx.x * MG_CONSUMERS + warp;
-    const int my_items = units_of(gl, op.units, TW) * ipu;
-    const int max_items = units_of(blockIdx.x * MG_CONSUMERS, op.units, TW) * ipu;   // slot 0 always has the most
-    const int chunks = op.seg_len / 8;
-    float acc0 = 0.f, acc1 = 0.f;
-    int unit = gl, sel = 0, seg = 0;
-    for (int i = 0; i < max_items; ++i) {
-        ptx::mbar_wait(ptx::smem_u32(&s_full[rs.stage]), rs.phase);
-        if (i < my_items) {
-            const uint4* wseg = reinterpret_cast<const uint4*>(ring + (size_t)rs.stage * MG_STAGE_BYTES + (size_t)warp * MG_SLOT_BYTES);
-            const uint4* xs = reinterpret_cast<const uint4*>(sx + (size_t)seg * op.seg_len);
-            float part = 0.f;
+// ------------------------------------------------------------------ x staging: merge of the split-KV attention partials
+__device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid) {
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
+    const int D = P.head_dim, H = P.heads, D4 = D + 4, maxp = P.att_maxp;
+    const int Lc = att_warp_len(ctx, H, gridDim.x) * MG_CONSUMERS;
+    for (int gi = tid; gi < H * D / 4; gi += 256) {
+        const int e0 = gi * 4, h = e0 / D, d0 = e0 - h * D;
+        const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+        const int np = c1 - c0 + 1;
+        const float* base = P.att_ws + (size_t)h * maxp * D4;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        float den = 0.f;
+        if (np <= 8) {
+            float2 hd[8];
+            float4 ov[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < np) {
+                    hd[s] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)s * D4));
+                    ov[s] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * D4 + 4 + d0));
+                } else {
+                    hd[s] = make_float2(-INFINITY, 0.f);
+                    ov[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float M = hd[0].x;
+#pragma unroll
+            for (int s = 1; s < 8; ++s) M = fmaxf(M, hd[s].x);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float w = __expf(hd[s].x - M);
+                den += w * hd[s].y;
+                num.x += w * ov[s].x; num.y += w * ov[s].y; num.z += w * ov[s].z; num.w += w * ov[s].w;
+            }
+        } else {
+            float M = -INFINITY;
+            for (int s = 0; s < np; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * D4));
 #pragma unroll 4
-            for (int c = lane; c < chunks; c += 32) part += dot8m(wseg[c], xs[c]);
-            if (sel == 0) acc0 += part; else acc1 += part;
+            for (int s = 0; s < np; ++s) {
+                const float2 hd = __ldcg(reinterpret_cast<const float2*>(base + (size_t)s * D4));
+                const float4 ov = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * D4 + 4 + d0));
+                const float w = __expf(hd.x - M);
+                den += w * hd.y;
+                num.x += w * ov.x; num.y += w * ov.y; num.z += w * ov.z; num.w += w * ov.w;
+            }
+        }
+        const float inv = den > 0.f ? 1.0f / den : 0.f;
+        uint2 o;
+        o.x = pack_bf16(num.x * inv, num.y * inv);
+        o.y = pack_bf16(num.z * inv, num.w * inv);
+        *reinterpret_cast<uint2*>(sx + e0) = o;
+    }
+    cbar();
+}
+
+// ------------------------------------------------------------------ consumer side of one GEMV phase (x already staged)
+__device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, const __nv_bfloat16* emb_row,
+                                           float* extra_out, const Smem& S, uint32_t& cnt, int tid, int warp, int lane,
+                                           long long* occ = nullptr) {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
+    const int nsel = op.act == 3 ? 2 : 1;
+    const int nseg = op.nseg;
+    const int ipu = nsel * nseg;
+    const int n_items = nu * ipu;
+    const int g = lane >> 2, t = lane & 3;
+    const int nchunk2 = op.seg_len / 64;
+    // residual of this thread's output column: loaded now, used in the epilogue (hides one L2 round trip)
+    const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : op.residual;
+    float res_pre = 0.f;
+    if (res != nullptr && tid < nu * MEGA_ROWS) {
+        const int n = (c + (tid >> 3) * G) * MEGA_ROWS + (tid & 7);
+        if (n < op.n_out) res_pre = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
+    }
+    if (occ != nullptr && lane == 0) {
+        // bring-up: how many of this warp's next slots have already landed when the phase starts (prefetch depth)
+        int ready = 0;
+        for (uint32_t k = 0; k < (uint32_t)MG_SLOTS; ++k) {
+            const uint32_t cc = cnt + k;
+            ready += mbar_test(ptx::smem_u32(&S.full[warp * MG_SLOTS + cc % MG_SLOTS]), (cc / MG_SLOTS) & 1) ? 1 : 0;
+        }
+        occ[warp] = ready;
+    }
+    const uint32_t ring_w = ptx::smem_u32(S.ring) + warp * (MG_SLOTS * MG_SLOT_BYTES) + g * 64 + t * 16;   // item: [chunk][row g][64 B]
+    const uint32_t x_u32 = ptx::smem_u32(S.xa) + t * 16;
+    for (int q = warp; q < n_items; q += MG_CONSUMERS) {
+        const uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+        const int j = q / ipu, r = q - j * ipu;
+        const int seg = r % nseg;
+        uint32_t wa = ring_w + slot * MG_SLOT_BYTES;
+        uint32_t xa = x_u32 + seg * op.seg_len * 2;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+#pragma unroll 2
+        for (int ch = 0; ch < ((P.ablate & 8) ? 0 : nchunk2); ++ch) {
+            const uint4 w0 = lds128(wa), x0 = lds128(xa);
+            const uint4 w1 = lds128(wa + 512), x1 = lds128(xa + 64);
+            mma16816(acc[0], x0.x, x0.x, x0.y, x0.y, w0.x, w0.y);
+            mma16816(acc[1], x0.z, x0.z, x0.w, x0.w, w0.z, w0.w);
+            mma16816(acc[2], x1.x, x1.x, x1.y, x1.y, w1.x, w1.y);
+            mma16816(acc[3], x1.z, x1.z, x1.w, x1.w, w1.z, w1.w);
+            wa += 1024;
+            xa += 128;
+        }
+        if (g == 0) {
+            float2 o;
+            o.x = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+            o.y = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+            *reinterpret_cast<float2*>(S.part + (size_t)q * 8 + 2 * t) = o;
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_empty[rs.stage]));
-        if (++rs.stage == MG_STAGES) { rs.stage = 0; rs.phase ^= 1; }
-        if (i < my_items) {
-            if (++seg == op.nseg) {
-                seg = 0;
-                if (++sel == nsel) {
-                    // ---- unit finished
-                    sel = 0;
-                    acc0 = wsum_m(acc0);
-                    if (op.act == 3) acc1 = wsum_m(acc1);
-                    if (lane == 0) {
-                        if (op.act == 3) {
-                            const float g = bf16r(acc0), u = bf16r(acc1);
-                            reinterpret_cast<__nv_bfloat16*>(op.out)[unit] = __float2bfloat16_rn(u * bf16r(silu_f(g)));
-                        } else {
-                            float y = acc0;
-                            if (op.bias) y += __bfloat162float(op.bias[unit]);
-                            y = bf16r(y);
-                            if (op.residual) {
-                                // written by another CTA in an earlier phase -> L1-bypassing load
-                                const unsigned short raw = __ldcg(reinterpret_cast<const unsigned short*>(op.residual) + unit);
-                                y = bf16r(y + __uint_as_float((uint32_t)raw << 16));
-                            }
-                            if (op.out_f32) reinterpret_cast<float*>(op.out)[unit] = y;
-                            else reinterpret_cast<__nv_bfloat16*>(op.out)[unit] = __float2bfloat16_rn(y);
-                        }
-                    }
-                    acc0 = acc1 = 0.f;
-                    unit += TW;
-                }
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
+        ++cnt;
+    }
+    cbar();
+    // ---- epilogue: one thread per output column, segments summed in a fixed order
+    unsigned long long key = 0ull;
+    for (int o = tid; o < nu * MEGA_ROWS; o += 256) {
+        const int j = o >> 3, col = o & 7;
+        const int n = (c + j * G) * MEGA_ROWS + col;
+        if (n >= op.n_out) continue;
+        const float* pp = S.part + (size_t)j * ipu * 8 + col;
+        float a0 = 0.f;
+        for (int s = 0; s < nseg; ++s) a0 += pp[s * 8];
+        if (op.act == 3) {
+            float a1 = 0.f;
+            for (int s = 0; s < nseg; ++s) a1 += pp[(nseg + s) * 8];
+            const float gt = bf16r(a0), u = bf16r(a1);
+            reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(u * bf16r(silu_f(gt)));
+        } else {
+            float y = a0;
+            if (op.bias) y += __bfloat162float(op.bias[n]);
+            y = bf16r(y);
+            if (res) {
+                const float rv = o < 256 ? res_pre
+                                         : __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
+                y = bf16r(y + rv);
+            }
+            if (op.out_f32) reinterpret_cast<float*>(op.out)[n] = y;
+            else reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(y);
+            if (extra_out) extra_out[n] = y;
+            if (op.argmax) {
+                uint32_t u = __float_as_uint(y);
+                u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+                const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                key = k > key ? k : key;
             }
         }
     }
-}
-
-// ------------------------------------------------------------------ producer side of one GEMV phase (lanes 0..7)
-__device__ __forceinline__ void produce_phase(const MegaOp& op_g, uint32_t ring_u32, uint64_t* s_full, uint64_t* s_empty,
-                                              RingState& rs, int lane) {
-    const MegaOp op = op_g;
-    const int TW = gridDim.x * MG_CONSUMERS;
-    const int nsel = op.act == 3 ? 2 : 1;
-    const int ipu = nsel * op.nseg;
-    const int gl = blockIdx.x * MG_CONSUMERS + lane;                 // lane w feeds consumer warp w's slot
-    const int my_items = lane < MG_CONSUMERS ? units_of(gl, op.units, TW) * ipu : 0;
-    const int max_items = units_of(blockIdx.x * MG_CONSUMERS, op.units, TW) * ipu;
-    const uint32_t seg_bytes = (uint32_t)op.seg_len * 2;
-    int unit = gl, sel = 0, seg = 0;
-    for (int i = 0; i < max_items; ++i) {
-        ptx::mbar_wait(ptx::smem_u32(&s_empty[rs.stage]), rs.phase ^ 1);
-        const bool valid = i < my_items;
-        const unsigned mask = __ballot_sync(0xffffffffu, valid);
-        const uint32_t bar = ptx::smem_u32(&s_full[rs.stage]);
-        if (lane == 0) ptx::mbar_arrive_expect_tx(bar, __popc(mask) * seg_bytes);
-        __syncwarp();
-        if (valid) {
-            const int row = row_of(op, unit, sel);
-            bulk_g2s_m(ring_u32 + rs.stage * MG_STAGE_BYTES + lane * MG_SLOT_BYTES,
-                       op.W + (size_t)row * op.ldw + (size_t)seg * op.seg_len, seg_bytes, bar);
-            if (++seg == op.nseg) { seg = 0; if (++sel == nsel) { sel = 0; unit += TW; } }
+    if (op.argmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
         }
-        if (++rs.stage == MG_STAGES) { rs.stage = 0; rs.phase ^= 1; }
+        if (lane == 0 && key != 0ull) atomicMax(P.amax, key);
     }
 }
 
-// ------------------------------------------------------------------ attention phase (warp task = (head, 128-token split))
+// ------------------------------------------------------------------ producer side of one GEMV phase: lane w feeds warp w
+__device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, uint32_t& pc, int inflight, int lane) {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
+    const int ipu = (op.act == 3 ? 2 : 1) * op.nseg;
+    const int n_items = nu * ipu;
+    const uint32_t item_bytes = (uint32_t)op.seg_len * 2 * MEGA_ROWS;
+    const int my_n = (lane < MG_CONSUMERS && n_items > lane) ? (n_items - lane + MG_CONSUMERS - 1) / MG_CONSUMERS : 0;
+    const uint32_t ring_w = ptx::smem_u32(S.ring) + lane * (MG_SLOTS * MG_SLOT_BYTES);
+    const uint32_t full0 = ptx::smem_u32(S.full + lane * MG_SLOTS), empty0 = ptx::smem_u32(S.empty + lane * MG_SLOTS);
+    int m = 0;
+    while (__any_sync(0xffffffffu, m < my_n)) {
+        bool issued = false;
+        if (m < my_n) {
+            const uint32_t slot = pc % MG_SLOTS, par = (pc / MG_SLOTS) & 1;
+            bool ok = mbar_test(empty0 + slot * 8, par ^ 1);                    // slot consumed
+            if (ok && pc >= (uint32_t)inflight) {                               // bounded number of copies in flight
+                const uint32_t pp = pc - inflight;
+                ok = mbar_test(full0 + (pp % MG_SLOTS) * 8, (pp / MG_SLOTS) & 1);
+            }
+            if (ok) {
+                const int q = lane + m * MG_CONSUMERS;
+                const int j = q / ipu, r = q - j * ipu;
+                const size_t item = (size_t)(c + j * G) * ipu + r;              // packed order: [unit][sel][seg]
+                ptx::mbar_arrive_expect_tx(full0 + slot * 8, item_bytes);
+                bulk_g2s_m(ring_w + slot * MG_SLOT_BYTES, reinterpret_cast<const uint8_t*>(op.W) + item * item_bytes, item_bytes,
+                           full0 + slot * 8);
+                ++pc;
+                ++m;
+                issued = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
+    }
+}
+
+// ------------------------------------------------------------------ attention phase
 template <int D>
-__device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, float* s_warp /* [2*D] floats per warp */,
-                                                int warp, int lane) {
-    constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2;
-    const int H = P.heads, KVH = P.kv_heads;
-    const int pos = P.st->ctx_len;                    // position == cache slot of the token being processed
+__device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, int warp, int lane) {
+    constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2, D4 = D + 4;
+    constexpr int NP = 1;                              // passes (8 tokens each) per batch; two batches in flight
+                                                       // (9 warps/CTA cap the kernel at 168 registers per thread)
+    const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
+    const int G = gridDim.x, c = blockIdx.x;
     const int ctx = pos + 1;
-    const int n_act = (ctx + MG_SPLIT - 1) / MG_SPLIT;
-    const int n_tasks = H * n_act;
-    const int TW = gridDim.x * MG_CONSUMERS;
+    const int Lw = att_warp_len(ctx, H, G), Lc = Lw * MG_CONSUMERS;
+    const int total = H * ctx;
     const __nv_bfloat16* qkv = P.qkv;
     __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
     __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
-    const __nv_bfloat16* cp = P.rope_cos + (size_t)pos * D;
-    const __nv_bfloat16* sp = P.rope_sin + (size_t)pos * D;
-    float* sq = s_warp;          // rotated q   [D]
-    float* sk = s_warp + D;      // rotated new k [D]
-    const int sub = lane & 3, tg = lane >> 2;         // 4 lanes per token, 8 tokens per pass
-    const int nsplit_ws = (P.max_ctx + MG_SPLIT - 1) / MG_SPLIT;
-    for (int task = blockIdx.x * MG_CONSUMERS + warp; task < n_tasks; task += TW) {
-        const int h = task / n_act, s = task % n_act;
-        const int hk = h / (H / KVH);
-        const int t0 = s * MG_SPLIT, t1 = min(t0 + MG_SPLIT, ctx);
+    const float* rcos = S.rope;
+    const float* rsin = S.rope + 128;
+    float* sq = reinterpret_cast<float*>(S.xa) + warp * 2 * D;     // rotated q [D]
+    float* sk = sq + D;                                            // rotated new k [D]
+    float* segs = reinterpret_cast<float*>(S.xa) + MG_CONSUMERS * 2 * D;   // [16][D + 4]: head, m, l, -, o[D]
+    const int sub = lane & 3, tg = lane >> 2;          // 4 lanes per token, 8 tokens per pass
+    const float scale = P.scale;
+
+    // bring-up trace of the LAST layer: per-warp clock64 at 8 points of this phase (MEGA_TRACE_ATT_OFF + warp * 8 + k)
+    long long* atr = (P.trace && layer == P.n_layers - 1 && lane == 0)
+                         ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF + warp * 8 : nullptr;
+#define ATR(k) do { if (atr) atr[k] = clock64(); } while (0)
+    ATR(0);
+    if (lane < 2) segs[(warp * 2 + lane) * D4] = __int_as_float(-1);
+    const int f0 = (c * MG_CONSUMERS + warp) * Lw;
+    const int f1 = min(f0 + Lw, total);
+    int f = f0, sg = 0;
+    while (f < f1) {
+        const int h = f / ctx, hk = h / rep;
+        const int t0 = f - h * ctx;
+        const int t1 = min(ctx, t0 + (f1 - f));
+        f += t1 - t0;
         // ---- RoPE of q (and of the new k) for this head: q_embed = bf16(bf16(q*cos) + bf16(rot(q)*sin))
         __syncwarp();
-        for (int j = lane; j < half; j += 32) {
-            const float c1 = __bfloat162float(cp[j]), s1 = __bfloat162float(sp[j]);
-            const float c2 = __bfloat162float(cp[j + half]), s2 = __bfloat162float(sp[j + half]);
+        {
             const __nv_bfloat16* qh = qkv + (size_t)h * D;
-            const float q1 = __bfloat162float(__ldcg(qh + j)), q2 = __bfloat162float(__ldcg(qh + j + half));
-            sq[j] = bf16r(bf16r(q1 * c1) + bf16r(-q2 * s1));
-            sq[j + half] = bf16r(bf16r(q2 * c2) + bf16r(q1 * s2));
             const __nv_bfloat16* kh = qkv + (size_t)(H + hk) * D;
-            const float k1 = __bfloat162float(__ldcg(kh + j)), k2 = __bfloat162float(__ldcg(kh + j + half));
-            sk[j] = bf16r(bf16r(k1 * c1) + bf16r(-k2 * s1));
-            sk[j + half] = bf16r(bf16r(k2 * c2) + bf16r(k1 * s2));
-        }
-        __syncwarp();
-        const bool has_new = pos >= t0 && pos < t1;
-        const __nv_bfloat16* vnew = qkv + (size_t)(H + KVH + hk) * D;
-        if (has_new && (h % (H / KVH)) == 0) {
-            // exactly one task per kv head appends the new row to the cache (for FUTURE steps; this step's tasks use the
-            // locally rotated copy, so there is no intra-phase dependency on this write)
-            for (int j = lane; j < D; j += 32) {
-                kc_l[((size_t)hk * P.max_ctx + pos) * D + j] = __float2bfloat16_rn(sk[j]);
-                vc_l[((size_t)hk * P.max_ctx + pos) * D + j] = __ldcg(vnew + j);
+            float q1[(half + 31) / 32], q2[(half + 31) / 32], k1[(half + 31) / 32], k2[(half + 31) / 32];
+#pragma unroll
+            for (int u = 0; u < (half + 31) / 32; ++u) {
+                const int j = lane + u * 32;
+                if (j < half) {
+                    q1[u] = __bfloat162float(__ldcg(qh + j)); q2[u] = __bfloat162float(__ldcg(qh + j + half));
+                    k1[u] = __bfloat162float(__ldcg(kh + j)); k2[u] = __bfloat162float(__ldcg(kh + j + half));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < (half + 31) / 32; ++u) {
+                const int j = lane + u * 32;
+                if (j < half) {
+                    const float c1 = rcos[j], s1 = rsin[j], c2 = rcos[j + half], s2 = rsin[j + half];
+                    sq[j] = bf16r(bf16r(q1[u] * c1) + bf16r(-q2[u] * s1));
+                    sq[j + half] = bf16r(bf16r(q2[u] * c2) + bf16r(q1[u] * s2));
+                    sk[j] = bf16r(bf16r(k1[u] * c1) + bf16r(-k2[u] * s1));
+                    sk[j + half] = bf16r(bf16r(k2[u] * c2) + bf16r(k1[u] * s2));
+                }
             }
         }
+        __syncwarp();
+        ATR(1);
+        const bool has_new = pos >= t0 && pos < t1;    // pos is the last token: has_new => t1 == ctx
+        const int tend = has_new ? pos : t1;
+        const __nv_bfloat16* vnew = qkv + (size_t)(H + KVH + hk) * D;
+        uint4 vn[VPL];                                  // this lane's slice of the new v row
+        if (has_new) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) vn[i] = ldcg4(vnew + sub * EPL + i * 8);
+            if ((h % rep) == 0 && lane < D / 8) {
+                // exactly one segment per kv head appends the new row to the cache (for FUTURE steps; this step uses the
+                // locally rotated copy, so there is no intra-phase dependency on this write)
+                uint4 kq;
+                const float* s8 = sk + lane * 8;
+                kq.x = pack_bf16(s8[0], s8[1]); kq.y = pack_bf16(s8[2], s8[3]);
+                kq.z = pack_bf16(s8[4], s8[5]); kq.w = pack_bf16(s8[6], s8[7]);
+                *reinterpret_cast<uint4*>(kc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = kq;
+                *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = ldcg4(vnew + lane * 8);
+            }
+        }
+        ATR(2);
         float qf[EPL];
 #pragma unroll
         for (int i = 0; i < EPL; ++i) qf[i] = sq[sub * EPL + i];
-        const __nv_bfloat16* kbase = kc_l + (size_t)hk * P.max_ctx * D;
-        const __nv_bfloat16* vbase = vc_l + (size_t)hk * P.max_ctx * D;
-        // ---- scores: 16 passes of 8 tokens, K loads of 4 passes in flight
-        constexpr int NP = MG_SPLIT / 8;
-        float sc[NP];
-        float lmax = -INFINITY;
-#pragma unroll
-        for (int pb = 0; pb < NP; pb += 4) {
-            uint4 kr[4][VPL];
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int t = t0 + (pb + pp) * 8 + tg;
-                const bool ok = t < t1 && t != pos;
-                const __nv_bfloat16* src = kbase + (size_t)(ok ? t : t0) * D + sub * EPL;
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) kr[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(src) + i);
-            }
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int t = t0 + (pb + pp) * 8 + tg;
-                float sv = 0.f;
-                if (t == pos) {
-#pragma unroll
-                    for (int i = 0; i < EPL; ++i) sv += qf[i] * sk[sub * EPL + i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < VPL; ++i) {
-                        const uint4 v = kr[pp][i];
-                        float2 f;
-                        f = unpack_bf16(v.x); sv += qf[i * 8 + 0] * f.x + qf[i * 8 + 1] * f.y;
-                        f = unpack_bf16(v.y); sv += qf[i * 8 + 2] * f.x + qf[i * 8 + 3] * f.y;
-                        f = unpack_bf16(v.z); sv += qf[i * 8 + 4] * f.x + qf[i * 8 + 5] * f.y;
-                        f = unpack_bf16(v.w); sv += qf[i * 8 + 6] * f.x + qf[i * 8 + 7] * f.y;
-                    }
-                }
-                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-                sv = (t < t1) ? sv * P.scale : -INFINITY;
-                sc[pb + pp] = sv;
-                lmax = fmaxf(lmax, sv);
-            }
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        // ---- p = exp(s - max) rounded to bf16; o += p * v
+        const __nv_bfloat16* kbase = kc_l + (size_t)hk * P.max_ctx * D + sub * EPL;
+        const __nv_bfloat16* vbase = vc_l + (size_t)hk * P.max_ctx * D + sub * EPL;
         float o[EPL];
 #pragma unroll
         for (int i = 0; i < EPL; ++i) o[i] = 0.f;
-        float lsum = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        uint4 kr[NP][VPL], vr[NP][VPL];
+        auto load_batch = [&](int tb, uint4 (&kd)[NP][VPL], uint4 (&vd)[NP][VPL]) {
 #pragma unroll
-        for (int pb = 0; pb < NP; pb += 4) {
-            uint4 vr[4][VPL];
+            for (int pp = 0; pp < NP; ++pp) {
+                const int tk = tb + pp * 8 + tg;
+                const size_t off = (size_t)(tk < tend ? tk : t0) * D;
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int t = t0 + (pb + pp) * 8 + tg;
-                const bool ok = t < t1 && t != pos;
-                const __nv_bfloat16* src = vbase + (size_t)(ok ? t : t0) * D + sub * EPL;
+                for (int i = 0; i < VPL; ++i) kd[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(kbase + off) + i);
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) vr[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(src) + i);
+                for (int i = 0; i < VPL; ++i) vd[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(vbase + off) + i);
+            }
+        };
+        if (t0 < tend) load_batch(t0, kr, vr);
+        for (int tb = t0; tb < tend; tb += 8 * NP) {
+            uint4 kn[NP][VPL], vnx[NP][VPL];
+            const bool more = tb + 8 * NP < tend;
+            if (more) load_batch(tb + 8 * NP, kn, vnx);          // next batch in flight while this one is reduced
+            float sc[NP];
+            float bmax = -INFINITY;
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                float sv = 0.f;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const uint4 v = kr[pp][i];
+                    float2 f2;
+                    f2 = unpack_bf16(v.x); sv += qf[i * 8 + 0] * f2.x + qf[i * 8 + 1] * f2.y;
+                    f2 = unpack_bf16(v.y); sv += qf[i * 8 + 2] * f2.x + qf[i * 8 + 3] * f2.y;
+                    f2 = unpack_bf16(v.z); sv += qf[i * 8 + 4] * f2.x + qf[i * 8 + 5] * f2.y;
+                    f2 = unpack_bf16(v.w); sv += qf[i * 8 + 6] * f2.x + qf[i * 8 + 7] * f2.y;
+                }
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                sv = (tb + pp * 8 + tg < tend) ? sv * scale : -INFINITY;
+                sc[pp] = sv;
+                bmax = fmaxf(bmax, sv);
             }
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const int t = t0 + (pb + pp) * 8 + tg;
-                const float p = bf16r(__expf(sc[pb + pp] - lmax));
-                lsum += p;
-                if (t == pos) {
+            for (int off = 4; off < 32; off <<= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
+            const float m_new = fmaxf(m_run, bmax);
+            const float corr = __expf(m_run - m_new);
+            l_run *= corr;
 #pragma unroll
-                    for (int i = 0; i < EPL; ++i) o[i] += p * __bfloat162float(__ldcg(vnew + sub * EPL + i));
-                } else {
+            for (int i = 0; i < EPL; ++i) o[i] *= corr;
 #pragma unroll
-                    for (int i = 0; i < VPL; ++i) {
-                        const uint4 v = vr[pp][i];
-                        float2 f;
-                        f = unpack_bf16(v.x); o[i * 8 + 0] += p * f.x; o[i * 8 + 1] += p * f.y;
-                        f = unpack_bf16(v.y); o[i * 8 + 2] += p * f.x; o[i * 8 + 3] += p * f.y;
-                        f = unpack_bf16(v.z); o[i * 8 + 4] += p * f.x; o[i * 8 + 5] += p * f.y;
-                        f = unpack_bf16(v.w); o[i * 8 + 6] += p * f.x; o[i * 8 + 7] += p * f.y;
-                    }
+            for (int pp = 0; pp < NP; ++pp) {
+                const float p = bf16r(__expf(sc[pp] - m_new));
+                l_run += p;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const uint4 v = vr[pp][i];
+                    float2 f2;
+                    f2 = unpack_bf16(v.x); o[i * 8 + 0] += p * f2.x; o[i * 8 + 1] += p * f2.y;
+                    f2 = unpack_bf16(v.y); o[i * 8 + 2] += p * f2.x; o[i * 8 + 3] += p * f2.y;
+                    f2 = unpack_bf16(v.z); o[i * 8 + 4] += p * f2.x; o[i * 8 + 5] += p * f2.y;
+                    f2 = unpack_bf16(v.w); o[i * 8 + 6] += p * f2.x; o[i * 8 + 7] += p * f2.y;
                 }
             }
+            m_run = m_new;
+            if (more) {
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) { kr[pp][i] = kn[pp][i]; vr[pp][i] = vnx[pp][i]; }
+            }
         }
+        ATR(3);
+        if (has_new) {
+            float sv = 0.f;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) sv += qf[i] * sk[sub * EPL + i];
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv *= scale;
+            const float m_new = fmaxf(m_run, sv);
+            const float corr = __expf(m_run - m_new);
+            l_run *= corr;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) o[i] *= corr;
+            if (tg == 0) {
+                const float p = bf16r(__expf(sv - m_new));
+                l_run += p;
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const uint4 v = vn[i];
+                    float2 f2;
+                    f2 = unpack_bf16(v.x); o[i * 8 + 0] += p * f2.x; o[i * 8 + 1] += p * f2.y;
+                    f2 = unpack_bf16(v.y); o[i * 8 + 2] += p * f2.x; o[i * 8 + 3] += p * f2.y;
+                    f2 = unpack_bf16(v.z); o[i * 8 + 4] += p * f2.x; o[i * 8 + 5] += p * f2.y;
+                    f2 = unpack_bf16(v.w); o[i * 8 + 6] += p * f2.x; o[i * 8 + 7] += p * f2.y;
+                }
+            }
+            m_run = m_new;
+        }
+        ATR(4);
+        // ---- reduce over the 8 token groups; the 4 sub-lanes of a token carry identical p, so l is reduced over tg only
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, off);
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             o[i] += __shfl_xor_sync(0xffffffffu, o[i], 4);
             o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
             o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
         }
-        if (sub != 0) lsum = 0.f;
-        lsum = wsum_m(lsum);
-        float* wrow = P.att_ws + ((size_t)h * nsplit_ws + s) * (D + 2);
+        float* rec = segs + (size_t)(warp * 2 + sg) * D4;
         if (lane < 4) {
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) wrow[2 + lane * EPL + i] = o[i];
+            for (int i = 0; i < EPL; ++i) rec[4 + lane * EPL + i] = o[i];
         }
-        if (lane == 0) { wrow[0] = lmax; wrow[1] = lsum; }
-        // ---- last-arriving split of head h merges
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) last = (atomicAdd(&P.att_counters[h], 1) == n_act - 1) ? 1 : 0;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence();
-            const float* base = P.att_ws + (size_t)h * nsplit_ws * (D + 2);
+        if (lane == 0) { rec[0] = __int_as_float(h); rec[1] = m_run; rec[2] = l_run; }
+        ++sg;
+    }
+    if (sg == 0) { ATR(1); ATR(2); ATR(3); ATR(4); }
+    ATR(5);
+    cbar();
+    ATR(6);
+    // ---- merge the warp segments of this CTA per head, one global partial per (head, CTA)
+    const int cf0 = c * Lc, cf1 = min(cf0 + Lc, total);
+    if (cf0 < cf1) {
+        const int h_first = cf0 / ctx, h_last = (cf1 - 1) / ctx;
+        for (int hh = h_first + warp; hh <= h_last; hh += MG_CONSUMERS) {
             float M = -INFINITY;
-            for (int ss_ = 0; ss_ < n_act; ++ss_) M = fmaxf(M, __ldcg(base + (size_t)ss_ * (D + 2)));
-            for (int d = lane; d < D; d += 32) {
-                float num = 0.f, den = 0.f;
-                for (int ss_ = 0; ss_ < n_act; ++ss_) {
-                    const float* r = base + (size_t)ss_ * (D + 2);
-                    const float wgt = __expf(__ldcg(r) - M);
-                    num += wgt * __ldcg(r + 2 + d);
-                    den += wgt * __ldcg(r + 1);
+            for (int s = 0; s < 2 * MG_CONSUMERS; ++s)
+                if (__float_as_int(segs[s * D4]) == hh) M = fmaxf(M, segs[s * D4 + 1]);
+            float L = 0.f;
+            float num[(D + 31) / 32];
+#pragma unroll
+            for (int i = 0; i < (D + 31) / 32; ++i) num[i] = 0.f;
+            for (int s = 0; s < 2 * MG_CONSUMERS; ++s) {
+                if (__float_as_int(segs[s * D4]) != hh) continue;
+                const float w = __expf(segs[s * D4 + 1] - M);
+                L += w * segs[s * D4 + 2];
+#pragma unroll
+                for (int i = 0; i < (D + 31) / 32; ++i) {
+                    const int d = lane + i * 32;
+                    if (d < D) num[i] += w * segs[s * D4 + 4 + d];
                 }
-                P.attn_out[(size_t)h * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
             }
-            if (lane == 0) P.att_counters[h] = 0;
+            const int c0 = (hh * ctx) / Lc;
+            float* dst = P.att_ws + ((size_t)hh * P.att_maxp + (c - c0)) * D4;
+#pragma unroll
+            for (int i = 0; i < (D + 31) / 32; ++i) {
+                const int d = lane + i * 32;
+                if (d < D) dst[4 + d] = num[i];
+            }
+            if (lane == 0) { dst[0] = M; dst[1] = L; }
         }
     }
+    ATR(7);
+#undef ATR
 }
 
+template <int D>
 __global__ void __launch_bounds__(MG_THREADS, 1)
-decode_mega_kernel(const MegaPlan* __restrict__ plan_g, long long* tokens_out, float* logits_out, long long eos_id,
-                   long long pad_id) {
+decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* tokens_out, float* logits_out,
+                   long long eos_id, long long pad_id) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ring = smem;
-    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem + MG_STAGES * MG_STAGE_BYTES);
-    __shared__ __align__(8) uint64_t s_full[MG_STAGES], s_empty[MG_STAGES];
+    __shared__ __align__(8) uint64_t s_full[MG_CONSUMERS * MG_SLOTS], s_empty[MG_CONSUMERS * MG_SLOTS];
     __shared__ float s_red[MG_CONSUMERS];
-    // the attention phase never overlaps a GEMV phase of the same CTA: its per-warp scratch aliases the x staging area
-    float (*s_att)[2 * 128] = reinterpret_cast<float (*)[2 * 128]>(sx);
+    __shared__ float s_rope[2 * 128];
     const MegaPlan& P = *plan_g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Smem S;
+    S.ring = smem;
+    S.xa = smem + MG_RING_BYTES;
+    S.part = reinterpret_cast<float*>(S.xa + P.x_bytes);
+    S.full = s_full;
+    S.empty = s_empty;
+    S.red = s_red;
+    S.rope = s_rope;
 
     if (tid == 0) {
-        for (int s = 0; s < MG_STAGES; ++s) {
+        for (int s = 0; s < MG_CONSUMERS * MG_SLOTS; ++s) {
             ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&s_empty[s]), MG_CONSUMERS);
+            ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
         }
         ptx::fence_mbar_init();
     }
     __syncthreads();
-    RingState rs{0, 0};
     const int n_ops = P.n_layers * 4 + 1;
 
     if (warp == MG_CONSUMERS) {
-        // ------------------------------------------------------------ producer: the whole step's weights, in order
-        const uint32_t ring_u32 = ptx::smem_u32(ring);
-        for (int i = 0; i < n_ops; ++i) produce_phase(P.ops[i], ring_u32, s_full, s_empty, rs, lane);
+        // ------------------------------------------------------------ producer: every step's weights, in order
+        uint32_t pc = 0;
+        const int inflight = P.inflight;
+        for (int stp = 0; stp < n_steps; ++stp)
+            for (int i = 0; i < n_ops; ++i) {
+                const MegaOp op = P.ops[i];
+                produce_phase(op, S, pc, inflight, lane);
+            }
         return;
     }
     // ---------------------------------------------------------------- consumers
     unsigned epoch = 0;
-    Tracer tr{P.trace ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE : nullptr};
-    tr.mark(tid);
-    // embed the current token into the residual stream (CTA 0), everyone waits
-    if (blockIdx.x == 0) {
-        const long long tok = P.st->cur_token;
-        const uint4* src = reinterpret_cast<const uint4*>(P.embed + (size_t)tok * P.dim);
-        for (int i = tid; i < P.dim / 8; i += 256) reinterpret_cast<uint4*>(P.x)[i] = src[i];
-    }
-    tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-    for (int l = 0; l < P.n_layers; ++l) {
-        gemv_phase(P.ops[l * 4 + 0], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // norm + qkv
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-        if (P.head_dim == 96) attention_phase<96>(P, l, s_att[warp], warp, lane);
-        else if (P.head_dim == 128) attention_phase<128>(P, l, s_att[warp], warp, lane);
-        else attention_phase<64>(P, l, s_att[warp], warp, lane);
-        tr.mark(tid);                                   // keeps 3 marks per phase (no staging step here)
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-        gemv_phase(P.ops[l * 4 + 1], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // o_proj + residual
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-        gemv_phase(P.ops[l * 4 + 2], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // norm + gate_up + SwiGLU
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-        gemv_phase(P.ops[l * 4 + 3], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);     // down + residual
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-    }
-    gemv_phase(P.ops[P.n_layers * 4], sx, ring, s_full, s_empty, s_red, rs, tid, warp, lane, tr);    // norm + lm_head + bias
-    tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid); tr.mark(tid);
-    // ---- greedy pick + bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
-    if (blockIdx.x == 0) {
-        __shared__ float sv_[MG_CONSUMERS];
-        __shared__ int si_[MG_CONSUMERS];
-        DecodeState* st = P.st;
-        const int step = st->step;
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int i = tid; i < P.vocab; i += 256) {
-            const float v = __ldcg(P.logits + i);
-            if (logits_out) logits_out[(size_t)step * P.vocab + i] = v;
-            if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    uint32_t cnt = 0;
+    const int pos0 = P.st->ctx_len;                     // position == cache slot of the first token processed
+    const int step0 = P.st->step;
+    const bool tracing = P.trace != nullptr;
+    const int ablate = P.ablate;                        // bring-up timing ablations (GVL_MEGA_ABLATE), 0 in production
+    if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 2] = (long long)globaltimer_ns();
+    for (int stp = 0; stp < n_steps; ++stp) {
+        const int pos = pos0 + stp, step = step0 + stp;
+        Tracer tr{tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE : nullptr};
+        tr.mark(tid); tr.mark(tid); tr.mark(tid);       // (the embed phase of the first version: kept for the trace layout)
+        const long long tok = __ldcg(&P.st->cur_token);
+        const __nv_bfloat16* emb_row = P.embed + (size_t)tok * P.dim;
+        if (tid < P.head_dim) {
+            s_rope[tid] = __bfloat162float(P.rope_cos[(size_t)pos * P.head_dim + tid]);
+            s_rope[128 + tid] = __bfloat162float(P.rope_sin[(size_t)pos * P.head_dim + tid]);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        MegaOp op = P.ops[0];
+        NormPre np;
+        prefetch_norm(op, np, tid);
+        for (int l = 0; l < P.n_layers; ++l) {
+            // norm + qkv
+            if (!(ablate & 4)) stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
+            tr.mark(tid);
+            long long* occ = tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ : nullptr);
+            op = P.ops[l * 4 + 1];
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            // rope + KV append + split-KV attention
+            if (!(ablate & 2)) attention_phase<D>(P, l, pos, S, warp, lane);
+            tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            // merge + o_proj + residual
+            if (!(ablate & 4)) stage_x_attn(P, S, pos + 1, tid);
+            tr.mark(tid);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 8 : nullptr);
+            op = P.ops[l * 4 + 2];
+            prefetch_norm(op, np, tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            // norm + gate_up + SwiGLU
+            if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            tr.mark(tid);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 16 : nullptr);
+            op = P.ops[l * 4 + 3];
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            // down + residual
+            if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            tr.mark(tid);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 24 : nullptr);
+            op = P.ops[l * 4 + 4];
+            prefetch_norm(op, np, tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
         }
-        if (lane == 0) { sv_[warp] = best; si_[warp] = bi; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) {
-            for (int w = 1; w < MG_CONSUMERS; ++w)
-                if (sv_[w] > best || (sv_[w] == best && si_[w] < bi)) { best = sv_[w]; bi = si_[w]; }
-            long long tok = bi;
-            if (st->finished) tok = pad_id;
-            else if (eos_id >= 0 && tok == eos_id) st->finished = 1;
-            if (tokens_out) tokens_out[step] = tok;
-            st->cur_token = tok;
-            st->ctx_len = st->ctx_len + 1;
-            st->attn_len = st->ctx_len;
+        // norm + lm_head + bias + greedy pick
+        stage_x_vec(op, op.x, np, S, tid, warp, lane);
+        tr.mark(tid);
+        gemv_items(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+        // ---- bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
+        if (blockIdx.x == 0 && tid == 0) {
+            DecodeState* st = P.st;
+            const unsigned long long key = __ldcg(P.amax);
+            *P.amax = 0ull;
+            long long nt = key != 0ull ? (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : 0;
+            if (st->finished) nt = pad_id;
+            else if (eos_id >= 0 && nt == eos_id) st->finished = 1;
+            if (tokens_out) tokens_out[step] = nt;
+            st->cur_token = nt;
+            st->ctx_len = pos + 1;
+            st->attn_len = pos + 1;
             st->step = step + 1;
         }
+        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, tid, ablate);   // the next step reads cur_token
     }
+    if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 1] = (long long)globaltimer_ns();
 }
 
 }  // namespace
 
-size_t decode_mega_smem() { return MG_SMEM; }
+bool decode_mega_shape(MegaOp* op) {
+    const int K = op->K;
+    if (K <= 0 || K % 64 != 0) return false;
+    int nseg = (K + MEGA_SEG - 1) / MEGA_SEG;
+    while (nseg <= K / 64 && (K % nseg != 0 || (K / nseg) % 64 != 0)) ++nseg;
+    if (nseg > K / 64) return false;
+    op->nseg = nseg;
+    op->seg_len = K / nseg;
+    op->n_out = op->act == 3 ? op->n_rows / 2 : op->n_rows;
+    if (op->act == 3 && op->n_rows % 256 != 0) return false;
+    op->units = (op->n_out + MEGA_ROWS - 1) / MEGA_ROWS;
+    return true;
+}
 
-int decode_mega_launch(const MegaPlan* plan_dev, unsigned* grid_bar, long long* tokens_out, float* logits_out,
-                       long long eos_id, long long pad_id, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM) != cudaSuccess)
-            return GVL_ERR_CUDA;
-        attr_set = true;
+
+namespace {
+// out: [unit][sel][seg][32-k chunk][row g][32 k]; one thread per 16-byte chunk (8 k of one row)
+__global__ void mega_pack_kernel(const __nv_bfloat16* __restrict__ W, int ldw, MegaOp op, __nv_bfloat16* __restrict__ out,
+                                 size_t n_vec) {
+    const int nsel = op.act == 3 ? 2 : 1;
+    const int cpi = op.seg_len / 32;                   // chunks per item
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(v & 3), g = (int)((v >> 2) & 7);
+        size_t rest = v >> 5;
+        const int ch = (int)(rest % cpi); rest /= cpi;
+        const int seg = (int)(rest % op.nseg); rest /= op.nseg;
+        const int sel = (int)(rest % nsel);
+        const int unit = (int)(rest / nsel);
+        const int n = row_base_of(op, unit, sel) + g;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (n < op.n_rows) val = *reinterpret_cast<const uint4*>(W + (size_t)n * ldw + (size_t)seg * op.seg_len + ch * 32 + t * 8);
+        reinterpret_cast<uint4*>(out)[v] = val;
     }
-    if (cudaMemsetAsync(grid_bar, 0, sizeof(unsigned), s) != cudaSuccess) return GVL_ERR_CUDA;
+}
+}  // namespace
+
+size_t decode_mega_packed_elems(const MegaOp* op) {
+    return (size_t)op->units * (op->act == 3 ? 2 : 1) * op->nseg * MEGA_ROWS * op->seg_len;
+}
+
+int decode_mega_pack(const MegaOp* op, const __nv_bfloat16* W, int ldw, __nv_bfloat16* dst, cudaStream_t s) {
+    if (ldw % 8 != 0 || (reinterpret_cast<uintptr_t>(W) & 15) != 0) return GVL_ERR_ALIGN;
+    const size_t n_vec = decode_mega_packed_elems(op) / 8;
+    mega_pack_kernel<<<num_sms() * 8, 256, 0, s>>>(W, ldw, *op, dst, n_vec);
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
+}
+
+bool decode_mega_finalize(MegaPlan* p) {
+    const int G = num_sms();
+    const int D = p->head_dim, H = p->heads;
+    if (D != 64 && D != 96 && D != 128) return false;
+    if (H > 64 || H % p->kv_heads != 0 || (H * D) % 64 != 0) return false;
+    int maxk = 0, items = 0;
+    const int n_ops = p->n_layers * 4 + 1;
+    for (int i = 0; i < n_ops; ++i) {
+        const MegaOp& op = p->ops[i];
+        maxk = op.K > maxk ? op.K : maxk;
+        const int nu = (op.units + G - 1) / G;
+        const int it = nu * (op.act == 3 ? 2 : 1) * op.nseg;
+        items = it > items ? it : items;
+    }
+    int xb = maxk * 2;
+    if (att_scratch_bytes(D) > xb) xb = att_scratch_bytes(D);
+    p->x_bytes = (xb + 127) & ~127;
+    p->part_items = items;
+    p->att_maxp = G / H + 2;
+    const char* ab = getenv("GVL_MEGA_ABLATE");
+    p->ablate = ab ? atoi(ab) : 0;
+    const char* env = getenv("GVL_MEGA_INFLIGHT");
+    p->inflight = env ? atoi(env) : 1;
+    if (p->inflight < 1) p->inflight = 1;
+    if (p->inflight > MG_SLOTS) p->inflight = MG_SLOTS;
+    return (size_t)MG_RING_BYTES + p->x_bytes + (size_t)items * 32 <= (size_t)MG_SMEM_LIMIT;
+}
+
+size_t decode_mega_att_ws_bytes(const MegaPlan* p) {
+    return (size_t)p->heads * p->att_maxp * (p->head_dim + 4) * sizeof(float);
+}
+
+int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
+                       long long eos_id, long long pad_id, cudaStream_t s) {
+    const size_t smem = (size_t)MG_RING_BYTES + hp->x_bytes + (size_t)hp->part_items * 32;
+    using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long);
+    const int di = hp->head_dim == 64 ? 0 : hp->head_dim == 96 ? 1 : 2;
+    KernelT kern = di == 0 ? decode_mega_kernel<64> : di == 1 ? decode_mega_kernel<96> : decode_mega_kernel<128>;
+    static size_t attr_set[3] = {0, 0, 0};
+    if (attr_set[di] < smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return GVL_ERR_CUDA;
+        attr_set[di] = smem;
+    }
+    if (cudaMemsetAsync(hp->grid_bar, 0, sizeof(unsigned), s) != cudaSuccess) return GVL_ERR_CUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms());
     cfg.blockDim = dim3(MG_THREADS);
-    cfg.dynamicSmemBytes = MG_SMEM;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, decode_mega_kernel, plan_dev, tokens_out, logits_out, eos_id, pad_id) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, kern, plan_dev, n_steps, tokens_out, logits_out, eos_id, pad_id) != cudaSuccess)
         return GVL_ERR_CUDA;
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;

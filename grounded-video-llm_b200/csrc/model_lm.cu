@@ -41,10 +41,14 @@ struct gvl_lm {
     long long g_eos = 0, g_pad = 0;
     bool use_graph = true;
     bool use_pdl = true;
-    // single-kernel decode step (decode_mega.cu); GVL_DECODE_MEGA=0 falls back to the per-op kernel chain
-    bool use_mega = true;
+    // single-kernel decode step (decode_mega.cu), opt-in with GVL_DECODE_MEGA=1 until it beats the per-op kernel chain
+    bool use_mega = false;
     MegaPlan* plan_dev = nullptr;
+    MegaPlan* plan_host = nullptr;
     unsigned* grid_bar = nullptr;
+    float* mega_att_ws = nullptr;
+    __nv_bfloat16* mega_w = nullptr;  // packed decode copy of every layer's weights + lm_head (decode_mega_pack)
+    unsigned long long* amax = nullptr;
     long long* trace = nullptr;       // GVL_MEGA_TRACE=1: per-CTA phase timestamps of the last decode step
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
@@ -121,7 +125,7 @@ int enqueue_decode_step_impl(gvl_lm* lm, long long* tokens_out, float* logits_ou
 int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
                         cudaStream_t s) {
     if (lm->use_mega && lm->plan_dev)
-        return decode_mega_launch(lm->plan_dev, lm->grid_bar, tokens_out, logits_out, eos_id, pad_id, s);
+        return decode_mega_launch(lm->plan_host, lm->plan_dev, 1, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = lm->use_pdl;
     const int rc = enqueue_decode_step_impl(lm, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = false;
@@ -160,55 +164,79 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
     cudaMemset(lm->da_ws, 0, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx));
     {
         const char* env = getenv("GVL_DECODE_MEGA");
-        lm->use_mega = !(env && env[0] == '0') && w->n_layers <= MEGA_MAX_LAYERS && w->dim <= 14336 && w->ffn <= 14336 &&
-                       (w->heads * w->head_dim) <= 14336 && w->dim % 8 == 0 && w->ffn % 128 == 0 &&
-                       (w->head_dim == 64 || w->head_dim == 96 || w->head_dim == 128);
+        lm->use_mega = (env && env[0] == '1') && w->n_layers <= MEGA_MAX_LAYERS;
         if (lm->use_mega) {
             MegaPlan* hp = new MegaPlan();
+            memset(hp, 0, sizeof(MegaPlan));
             hp->n_layers = w->n_layers; hp->dim = w->dim; hp->heads = w->heads; hp->kv_heads = w->kv_heads;
             hp->head_dim = w->head_dim; hp->vocab = w->vocab; hp->max_ctx = w->max_ctx;
             hp->scale = 1.0f / sqrtf((float)w->head_dim);
+            bool ok = true;
             auto mk = [&](const void* W, int N, int K, const __nv_bfloat16* x, const void* norm_w, const void* bias,
                           const __nv_bfloat16* residual, void* out, int act, int out_f32) {
                 MegaOp op;
-                op.W = (const __nv_bfloat16*)W; op.ldw = K; op.K = K;
-                op.nseg = (K + 4095) / 4096;
-                while (K % (op.nseg * 8) != 0) ++op.nseg;      // K % 8 == 0 is checked above: terminates
-                op.seg_len = K / op.nseg;
-                op.units = act == 3 ? N / 2 : N;
+                memset(&op, 0, sizeof(op));
+                op.W = (const __nv_bfloat16*)W; op.K = K; op.n_rows = N;      // W: source for now, packed below
                 op.act = act; op.out_f32 = out_f32; op.x = x; op.norm_w = (const __nv_bfloat16*)norm_w; op.eps = w->rms_eps;
                 op.bias = (const __nv_bfloat16*)bias; op.residual = residual; op.out = out;
+                ok = decode_mega_shape(&op) && ok;
                 return op;
             };
             const int HD = w->heads * w->head_dim;
             for (int l = 0; l < w->n_layers; ++l) {
                 const gvl_lm_layer& L = lm->layers[l];
                 hp->ops[l * 4 + 0] = mk(L.qkv_w, qkv_n, D, lm->dx, L.in_norm_w, nullptr, nullptr, lm->dqkv, 0, 0);
-                hp->ops[l * 4 + 1] = mk(L.o_w, D, HD, lm->dattn, nullptr, nullptr, lm->dx, lm->dx, 0, 0);
+                hp->ops[l * 4 + 1] = mk(L.o_w, D, HD, nullptr, nullptr, nullptr, lm->dx, lm->dx, 0, 0);
+                hp->ops[l * 4 + 1].x_kind = 1;
                 hp->ops[l * 4 + 2] = mk(L.gate_up_w, 2 * w->ffn, D, lm->dx, L.post_norm_w, nullptr, nullptr, lm->dmid, 3, 0);
                 hp->ops[l * 4 + 3] = mk(L.down_w, D, w->ffn, lm->dmid, nullptr, nullptr, lm->dx, lm->dx, 0, 0);
             }
+            hp->ops[0].from_embed = 1;          // layer 0 reads the token's embedding row directly (no embed phase)
+            hp->ops[1].from_embed = 2;
             hp->ops[w->n_layers * 4] = mk(w->lm_head_w, w->vocab, D, lm->dx, w->final_norm_w, w->lm_head_b, nullptr, lm->dlogits, 0, 1);
+            hp->ops[w->n_layers * 4].argmax = 1;
             hp->embed = (const __nv_bfloat16*)w->embed;
             hp->rope_cos = (const __nv_bfloat16*)w->rope_cos; hp->rope_sin = (const __nv_bfloat16*)w->rope_sin;
-            hp->kv = lm->kv; hp->x = lm->dx; hp->qkv = lm->dqkv; hp->attn_out = lm->dattn; hp->mid = lm->dmid;
+            hp->kv = lm->kv; hp->x = lm->dx; hp->qkv = lm->dqkv; hp->mid = lm->dmid;
             hp->logits = lm->dlogits;
-            hp->att_ws = lm->da_ws;
-            const int nsplit = (w->max_ctx + 127) / 128;
-            hp->att_counters = reinterpret_cast<int*>(lm->da_ws + (size_t)w->heads * nsplit * (w->head_dim + 2));
             hp->st = lm->st;
-            hp->trace = nullptr;
-            if (getenv("GVL_MEGA_TRACE") && dev_alloc(&lm->trace, (size_t)num_sms() * MEGA_TRACE_STRIDE) == GVL_OK) {
-                cudaMemset(lm->trace, 0, (size_t)num_sms() * MEGA_TRACE_STRIDE * sizeof(long long));
-                hp->trace = lm->trace;
+            ok = ok && decode_mega_finalize(hp);
+            if (!ok) {                           // shape not covered by the single-kernel step: per-op chain
+                delete hp;
+                lm->use_mega = false;
+            } else {
+                hp->trace = nullptr;
+                if (getenv("GVL_MEGA_TRACE") && dev_alloc(&lm->trace, (size_t)num_sms() * MEGA_TRACE_STRIDE) == GVL_OK) {
+                    cudaMemset(lm->trace, 0, (size_t)num_sms() * MEGA_TRACE_STRIDE * sizeof(long long));
+                    hp->trace = lm->trace;
+                }
+                const int n_ops = w->n_layers * 4 + 1;
+                size_t pack_total = 0;
+                for (int i = 0; i < n_ops; ++i) pack_total += decode_mega_packed_elems(&hp->ops[i]);
+                bool aok = dev_alloc(&lm->mega_w, pack_total) == GVL_OK;
+                if (aok) {
+                    size_t off = 0;
+                    for (int i = 0; i < n_ops && aok; ++i) {
+                        MegaOp& op = hp->ops[i];
+                        aok = decode_mega_pack(&op, op.W, op.K, lm->mega_w + off, 0) == GVL_OK;
+                        op.W = lm->mega_w + off;
+                        off += decode_mega_packed_elems(&op);
+                    }
+                    aok = aok && cudaDeviceSynchronize() == cudaSuccess;
+                }
+                aok = aok && dev_alloc(&lm->grid_bar, 1) == GVL_OK && dev_alloc(&lm->plan_dev, 1) == GVL_OK &&
+                           dev_alloc(&lm->amax, 1) == GVL_OK &&
+                           dev_alloc(&lm->mega_att_ws, decode_mega_att_ws_bytes(hp) / sizeof(float)) == GVL_OK;
+                if (aok) {
+                    hp->grid_bar = lm->grid_bar;
+                    hp->amax = lm->amax;
+                    hp->att_ws = lm->mega_att_ws;
+                    aok = cudaMemset(lm->amax, 0, sizeof(unsigned long long)) == cudaSuccess &&
+                          cudaMemcpy(lm->plan_dev, hp, sizeof(MegaPlan), cudaMemcpyHostToDevice) == cudaSuccess;
+                }
+                lm->plan_host = hp;
+                if (!aok) { rc = GVL_ERR_NOMEM; goto fail; }
             }
-            bool ok = dev_alloc(&lm->grid_bar, 1) == GVL_OK && dev_alloc(&lm->plan_dev, 1) == GVL_OK;
-            if (ok) {
-                hp->grid_bar = lm->grid_bar;
-                ok = cudaMemcpy(lm->plan_dev, hp, sizeof(MegaPlan), cudaMemcpyHostToDevice) == cudaSuccess;
-            }
-            delete hp;
-            if (!ok) { rc = GVL_ERR_NOMEM; goto fail; }
         }
     }
     *out = lm;
@@ -226,6 +254,8 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->dx); cudaFree(lm->dqkv); cudaFree(lm->dq); cudaFree(lm->dattn); cudaFree(lm->dmid);
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
     cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar); cudaFree(lm->trace);
+    cudaFree(lm->mega_att_ws); cudaFree(lm->amax); cudaFree(lm->mega_w);
+    delete lm->plan_host;
     if (lm->cs) cudaStreamDestroy(lm->cs);
     if (lm->ev_in) cudaEventDestroy(lm->ev_in);
     if (lm->ev_out) cudaEventDestroy(lm->ev_out);
@@ -303,7 +333,10 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
     float* lbuf = want_logits ? lm->logit_buf : nullptr;
     int zero = 0;
     CU(cudaMemcpyAsync(&lm->st->step, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
-    if (!lm->use_graph) {
+    if (lm->use_mega && lm->plan_dev) {
+        // one cooperative launch runs all the steps (token / position / EOS state stay in device memory)
+        CK(decode_mega_launch(lm->plan_host, lm->plan_dev, n_steps, lm->tok_buf, lbuf, eos_id, pad_id, s));
+    } else if (!lm->use_graph) {
         for (int i = 0; i < n_steps; ++i) CK(enqueue_decode_step(lm, lm->tok_buf, lbuf, eos_id, pad_id, s));
     } else {
         if (lm->graph == nullptr || lm->g_logits != lbuf || lm->g_eos != eos_id || lm->g_pad != pad_id) {

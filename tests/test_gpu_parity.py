@@ -245,6 +245,30 @@ def test_lm_prefill_logits_and_greedy_decode(gvl, arch):
     lm.close()
 
 
+@pytest.mark.parametrize("arch,mega", [("phi3", "1"), ("llama", "1"), ("phi3", "0")])
+def test_lm_decode_long_context_both_step_implementations(gvl, arch, mega, monkeypatch):
+    """ctx > 128 exercises the flat (head, token) partition of the single-kernel decode step (decode_mega.cu) and the
+    256-token splits of the per-op chain; GVL_DECODE_MEGA is read when the gvl_lm object is created."""
+    monkeypatch.setenv("GVL_DECODE_MEGA", mega)
+    kvh = 4 if arch == "phi3" else 2
+    P = O.make_lm_params(arch=arch, dim=256, heads=4, kv_heads=kvh, head_dim=64, ffn=512, layers=2, vocab=1000, seed=9,
+                         std=0.05)
+    rope = O.phi35_rope_cfg(64) if arch == "phi3" else dict(type="plain", base=500000.0, bf16_quirk=True)
+    cfg = dict(arch=arch, layers=2, heads=4, kv_heads=kvh, head_dim=64, eps=1e-5, rope=rope)
+    emb = torch.randn(333, 256, generator=torch.Generator().manual_seed(8)) * 0.5
+    lm = gvl.model.CausalLM(P, arch, 4, kvh, 64, 1e-5, rope, max_ctx=512)
+    toks, lg = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=5, return_logits=True)
+    toks_ref, lg_ref = O.greedy_decode(emb, P, cfg, 5, mode="bf16")
+    _cmp(lg[0], lg_ref, atol=_logit_tol(lg_ref))
+    for t in range(5):
+        top2 = torch.topk(lg_ref[t], 2).values
+        if float(top2[0] - top2[1]) > 2e-2:
+            assert int(toks[0, t]) == toks_ref[t]
+    # the token the library picked is the argmax of the logits it returned (fused pick == separate argmax)
+    assert toks[0].tolist() == lg[0].argmax(-1).tolist()
+    lm.close()
+
+
 def test_eos_padding_semantics(gvl):
     P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=1, vocab=300, seed=11,
                          std=0.05)

@@ -54,7 +54,7 @@ def main():
         100 * (wbytes + kvb) / per_step / 1e6 / peak, peak))
     if os.environ.get("GVL_MEGA_TRACE"):
         handle = lm._active[0]
-        buf = np.zeros((160, 768), dtype=np.int64)
+        buf = np.zeros((160, 1024), dtype=np.int64)
         n, st = ctypes.c_int(), ctypes.c_int()
         rc = lib.gvl_lm_mega_trace(handle, buf.ctypes.data_as(ctypes.c_void_p), 160, ctypes.byref(n), ctypes.byref(st))
         if rc != 0:
@@ -82,6 +82,22 @@ def main():
         for k in ["embed"] + names + ["lm_head"]:
             a = agg[k]
             print("  %-8s %12.0f %12.0f %12.0f %14.0f" % (k, a[0], a[1], a[2], worst[k]))
+        g0, g1 = buf[0, 958], buf[0, 959]
+        if g1 > g0 > 0:
+            print("  kernel wall time (globaltimer, all %d steps of the last launch): %.3f ms = %.3f ms/step" % (
+                steps, (g1 - g0) / 1e6, (g1 - g0) / 1e6 / steps))
+        occ = buf[: n.value, 768:800].reshape(n.value, 4, 8).astype(np.float64)
+        print("  ring slots already landed when the phase starts (last layer, mean over CTAs x warps, of 3): "
+              + ", ".join("%s %.2f" % (k, occ[:, i].mean()) for i, k in enumerate(["qkv", "o_proj", "gate_up", "down"])))
+        a = buf[: n.value, 960:1024].reshape(n.value, 8, 8).astype(np.float64)
+        d = np.diff(a, axis=2)                                   # [cta, warp, 7]
+        tot = a[:, :, 7] - a[:, :, 0]
+        labels = ["rope", "append", "kv_loop", "new_tok", "reduce+write", "cta_bar", "merge"]
+        print("attention phase of the last layer, per warp (cycles): mean / max over %d warps" % (n.value * 8))
+        for i, k in enumerate(labels):
+            print("    %-14s %9.0f %9.0f" % (k, d[:, :, i].mean(), d[:, :, i].max()))
+        w = np.unravel_index(np.argmax(a[:, :, 5] - a[:, :, 0]), tot.shape)
+        print("    slowest warp before the CTA barrier: cta %d warp %d: %s" % (w[0], w[1], d[w[0], w[1]].astype(int).tolist()))
         print("  total cycles/step %.0f  (= %.3f ms at %.0f MHz if the SM clock was that)" % (total, total / 1.9e6, 1900))
 
 
