@@ -40,7 +40,7 @@ namespace gvl {
 namespace {
 
 constexpr int MG_CONSUMERS = 8;
-constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 1);
+constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 2);          // 8 consumer warps, ring producer, L2 prefetcher
 constexpr int MG_SLOT_BYTES = MEGA_ROWS * MEGA_SEG * 2;          // 8192: one packed item
 constexpr int MG_SLOTS = 3;                                      // ring depth per consumer warp
 constexpr int MG_RING_BYTES = MG_CONSUMERS * MG_SLOTS * MG_SLOT_BYTES;   // 196608
@@ -54,11 +54,21 @@ __host__ __device__ inline int att_warp_len(int ctx, int H, int G) {
     return (per + 7) & ~7;
 }
 __host__ __device__ inline int att_scratch_bytes(int D) { return MG_CONSUMERS * 2 * D * 4 + 2 * MG_CONSUMERS * (D + 4) * 4; }
+// K / V rows of a (head, token range) are contiguous in the cache, so they travel through the same per-warp rings as the
+// weights: a segment of `len` cached tokens is cut evenly into chunks of <= ct_max tokens (one ring slot), multiple of 8
+__host__ __device__ inline int att_chunk_len(int len, int ct_max) {
+    const int nch = (len + ct_max - 1) / ct_max;
+    return (((len + nch - 1) / nch) + 7) & ~7;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_g2s_m(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
     uint32_t ok;
@@ -103,10 +113,14 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 consumer threads
 
 // consumers-only grid barrier
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid, int ablate = 0) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid, volatile unsigned* cta_epoch,
+                                             int ablate = 0) {
     cbar();
-    if (ablate & 1) return;                          // timing ablation only (results are wrong)
     ++epoch;
+    if (ablate & 1) {                                // timing ablation only (results are wrong)
+        if (tid == 0) *cta_epoch = epoch;
+        return;
+    }
     if (tid == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
@@ -120,6 +134,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
                 }
             }
         }
+        __threadfence_block();
+        *cta_epoch = epoch;                          // the producer warp gates its K / V stream on this (produce_attention)
     }
     cbar();
 }
@@ -392,11 +408,23 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
 }
 
 // ------------------------------------------------------------------ producer side of one GEMV phase: lane w feeds warp w
-__device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, uint32_t& pc, int inflight, int lane) {
+__device__ __forceinline__ int cta_items(const MegaOp& op) {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
+    return nu * (op.act == 3 ? 2 : 1) * op.nseg;
+}
+
+// `inflight` copies per lane while the phase is still ahead of the consumers (pure prefetch: deep queues only delay the
+// latency-critical loads of the phase boundary the consumers are in), `inflight_cur` once the consumers have reached
+// this phase (cta_epoch >= my_epoch) and are waiting for exactly these items.
+__device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, uint32_t& pc, int inflight, int inflight_cur,
+                                              volatile unsigned* cta_epoch, unsigned my_epoch, int lane,
+                                              volatile unsigned* prod_ord, unsigned ord_base) {
     const int G = gridDim.x, c = blockIdx.x;
     const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
     const int ipu = (op.act == 3 ? 2 : 1) * op.nseg;
     const int n_items = nu * ipu;
+    if (lane == 0) *prod_ord = ord_base;               // progress in this CTA's item order, read by the L2 prefetcher
     const uint32_t item_bytes = (uint32_t)op.seg_len * 2 * MEGA_ROWS;
     const int my_n = (lane < MG_CONSUMERS && n_items > lane) ? (n_items - lane + MG_CONSUMERS - 1) / MG_CONSUMERS : 0;
     const uint32_t ring_w = ptx::smem_u32(S.ring) + lane * (MG_SLOTS * MG_SLOT_BYTES);
@@ -407,8 +435,9 @@ __device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, u
         if (m < my_n) {
             const uint32_t slot = pc % MG_SLOTS, par = (pc / MG_SLOTS) & 1;
             bool ok = mbar_test(empty0 + slot * 8, par ^ 1);                    // slot consumed
-            if (ok && pc >= (uint32_t)inflight) {                               // bounded number of copies in flight
-                const uint32_t pp = pc - inflight;
+            const uint32_t inf = *cta_epoch >= my_epoch ? inflight_cur : inflight;
+            if (ok && pc >= inf) {                                              // bounded number of copies in flight
+                const uint32_t pp = pc - inf;
                 ok = mbar_test(full0 + (pp % MG_SLOTS) * 8, (pp / MG_SLOTS) & 1);
             }
             if (ok) {
@@ -421,6 +450,133 @@ __device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, u
                 ++pc;
                 ++m;
                 issued = true;
+                if (lane == 0) *prod_ord = ord_base + (unsigned)m * MG_CONSUMERS;
+            }
+        }
+        if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
+    }
+}
+
+// ------------------------------------------------------------------ L2 prefetcher (10th warp)
+// The rings hold 28 MB, i.e. ~4 us of HBM stream, but a phase boundary (epilogue stores -> grid barrier -> activation
+// staging) lasts longer than that, so with the rings alone HBM idles at every boundary. This warp walks the same item
+// order as the producer and issues cp.async.bulk.prefetch.L2 for items up to `win` items (8 KB each) ahead of it: HBM ->
+// L2 keeps streaming while the rings are full, and after the boundary the ring refills from L2 instead of HBM.
+__device__ __forceinline__ void pf_throttle(volatile unsigned* prod_ord, unsigned my_ord, int win) {
+    while ((int)(my_ord - *prod_ord) > win) __nanosleep(200);
+}
+__device__ __forceinline__ void prefetch_phase(const MegaOp& op, volatile unsigned* prod_ord, unsigned ord_base, int win, int lane) {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int ipu = (op.act == 3 ? 2 : 1) * op.nseg;
+    const int n_items = cta_items(op);
+    const uint32_t item_bytes = (uint32_t)op.seg_len * 2 * MEGA_ROWS;
+    for (int q0 = 0; q0 < n_items; q0 += 32) {
+        if ((int)(ord_base + q0 + 32 - *prod_ord) <= 0) continue;      // the producer is already past this batch
+        pf_throttle(prod_ord, ord_base + q0, win);
+        const int q = q0 + lane;
+        if (q < n_items) {
+            const int j = q / ipu, r = q - j * ipu;
+            const size_t item = (size_t)(c + j * G) * ipu + r;
+            l2_prefetch(reinterpret_cast<const uint8_t*>(op.W) + item * item_bytes, item_bytes);
+        }
+    }
+}
+template <int D>
+__device__ __forceinline__ void prefetch_attention(const MegaPlan& P, int layer, int pos, volatile unsigned* prod_ord,
+                                                   unsigned ord_base, int win, int lane) {
+    pf_throttle(prod_ord, ord_base, win);
+    if (lane >= MG_CONSUMERS) return;
+    const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
+    const int ctx = pos + 1;
+    const int Lw = att_warp_len(ctx, H, gridDim.x);
+    const int total = H * ctx;
+    const __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
+    const __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
+    int f = (blockIdx.x * MG_CONSUMERS + lane) * Lw;
+    const int f1 = min(f + Lw, total);
+    while (f < f1) {
+        const int h = f / ctx;
+        const int t0 = f - h * ctx;
+        const int t1 = min(ctx, t0 + (f1 - f));
+        f += t1 - t0;
+        const int te = min(t1, pos);
+        if (te > t0) {
+            const size_t off = ((size_t)(h / rep) * P.max_ctx + t0) * D;
+            l2_prefetch(kc_l + off, (uint32_t)(te - t0) * D * 2);
+            l2_prefetch(vc_l + off, (uint32_t)(te - t0) * D * 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ producer side of the attention phase: lane w feeds warp w
+// the K / V chunks of its (head, token) range, in exactly the order attention_phase consumes them
+template <int D>
+__device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, int pos, const Smem& S, uint32_t& pc, int inflight,
+                                                  int inflight_cur, unsigned my_epoch, int lane, volatile unsigned* cta_epoch,
+                                                  unsigned need_epoch) {
+    constexpr int ROWB = D * 2, CTM = (MG_SLOT_BYTES / ROWB) & ~7;
+    const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int ctx = pos + 1;
+    const int Lw = att_warp_len(ctx, H, G);
+    const int total = H * ctx;
+    const __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
+    const __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
+    int f = 0, f1 = 0;
+    if (lane < MG_CONSUMERS) {
+        f = (c * MG_CONSUMERS + lane) * Lw;
+        f1 = min(f + Lw, total);
+    }
+    int tb = 0, tend = 0, cs = 8, hk = 0, is_v = 0;
+    auto next_seg = [&]() -> bool {
+        while (f < f1) {
+            const int h = f / ctx;
+            const int t0 = f - h * ctx;
+            const int t1 = min(ctx, t0 + (f1 - f));
+            f += t1 - t0;
+            const int te = min(t1, pos);                 // the new token (pos) never comes from the cache
+            if (te > t0) {
+                tb = t0; tend = te; hk = h / rep; is_v = 0;
+                cs = att_chunk_len(te - t0, CTM);
+                return true;
+            }
+        }
+        return false;
+    };
+    bool active = next_seg();
+    const uint32_t ring_w = ptx::smem_u32(S.ring) + lane * (MG_SLOTS * MG_SLOT_BYTES);
+    const uint32_t full0 = ptx::smem_u32(S.full + lane * MG_SLOTS), empty0 = ptx::smem_u32(S.empty + lane * MG_SLOTS);
+    // Rows appended by the previous step of this launch are part of this stream: wait until this CTA's consumers are past
+    // the grid barrier that followed that step's attention phase of this layer. A warp without GEMV items in between
+    // (tiny models) would otherwise let its ring run ahead of the append; at production sizes the wait never spins.
+    while (*cta_epoch < need_epoch) __nanosleep(100);
+    __threadfence_block();
+    fence_proxy_async_global();
+    while (__any_sync(0xffffffffu, active)) {
+        bool issued = false;
+        if (active) {
+            const uint32_t slot = pc % MG_SLOTS, par = (pc / MG_SLOTS) & 1;
+            bool ok = mbar_test(empty0 + slot * 8, par ^ 1);
+            const uint32_t inf = *cta_epoch >= my_epoch ? inflight_cur : inflight;
+            if (ok && pc >= inf) {
+                const uint32_t pp = pc - inf;
+                ok = mbar_test(full0 + (pp % MG_SLOTS) * 8, (pp / MG_SLOTS) & 1);
+            }
+            if (ok) {
+                const int n = min(cs, tend - tb);
+                const uint32_t bytes = (uint32_t)n * ROWB;
+                const __nv_bfloat16* src = (is_v ? vc_l : kc_l) + ((size_t)hk * P.max_ctx + tb) * D;
+                ptx::mbar_arrive_expect_tx(full0 + slot * 8, bytes);
+                bulk_g2s_m(ring_w + slot * MG_SLOT_BYTES, src, bytes, full0 + slot * 8);
+                ++pc;
+                issued = true;
+                if (is_v) {
+                    tb += cs;
+                    is_v = 0;
+                    if (tb >= tend) active = next_seg();
+                } else {
+                    is_v = 1;
+                }
             }
         }
         if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
@@ -429,10 +585,10 @@ __device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, u
 
 // ------------------------------------------------------------------ attention phase
 template <int D>
-__device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, int warp, int lane) {
+__device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, uint32_t& cnt, int warp,
+                                                int lane) {
     constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2, D4 = D + 4;
-    constexpr int NP = 1;                              // passes (8 tokens each) per batch; two batches in flight
-                                                       // (9 warps/CTA cap the kernel at 168 registers per thread)
+    constexpr int ROWB = D * 2, CTM = (MG_SLOT_BYTES / ROWB) & ~7, NPASS = CTM / 8;   // tokens / 8-token passes per ring item
     const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
     const int G = gridDim.x, c = blockIdx.x;
     const int ctx = pos + 1;
@@ -507,82 +663,89 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                 kq.z = pack_bf16(s8[4], s8[5]); kq.w = pack_bf16(s8[6], s8[7]);
                 *reinterpret_cast<uint4*>(kc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = kq;
                 *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = ldcg4(vnew + lane * 8);
+                fence_proxy_async_global();        // later steps read this row with bulk copies (async proxy)
             }
         }
         ATR(2);
         float qf[EPL];
 #pragma unroll
         for (int i = 0; i < EPL; ++i) qf[i] = sq[sub * EPL + i];
-        const __nv_bfloat16* kbase = kc_l + (size_t)hk * P.max_ctx * D + sub * EPL;
-        const __nv_bfloat16* vbase = vc_l + (size_t)hk * P.max_ctx * D + sub * EPL;
         float o[EPL];
 #pragma unroll
         for (int i = 0; i < EPL; ++i) o[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
-        uint4 kr[NP][VPL], vr[NP][VPL];
-        auto load_batch = [&](int tb, uint4 (&kd)[NP][VPL], uint4 (&vd)[NP][VPL]) {
+        // cached tokens [t0, tend): K chunk, then V chunk of the same tokens, from this warp's ring (produce_attention
+        // issues the identical sequence). Row r of an item sits at r * ROWB; lane (tg, sub) reads 16-byte pieces at
+        // tg * ROWB + sub * EPL * 2 + 16 i: conflict-free for D = 96 (8-lane phases hit 8 distinct 16-byte bank groups).
+        if (t0 < tend) {
+            const int cs = att_chunk_len(tend - t0, CTM);
+            const uint32_t ring_w = ptx::smem_u32(S.ring) + warp * (MG_SLOTS * MG_SLOT_BYTES) + sub * (EPL * 2);
+            for (int tb = t0; tb < tend; tb += cs) {
+                const int n = min(cs, tend - tb);
+                uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
+                ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+                uint32_t base = ring_w + slot * MG_SLOT_BYTES;
+                float sc[NPASS];
+                float bmax = -INFINITY;
 #pragma unroll
-            for (int pp = 0; pp < NP; ++pp) {
-                const int tk = tb + pp * 8 + tg;
-                const size_t off = (size_t)(tk < tend ? tk : t0) * D;
+                for (int pp = 0; pp < NPASS; ++pp) {
+                    sc[pp] = -INFINITY;
+                    if (pp * 8 < n) {
+                        const int r = pp * 8 + tg;
+                        const bool valid = r < n;
+                        const uint32_t a = base + (valid ? r : 0) * ROWB;
+                        float sv = 0.f;
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) kd[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(kbase + off) + i);
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) vd[pp][i] = ldg_stream4(reinterpret_cast<const uint4*>(vbase + off) + i);
-            }
-        };
-        if (t0 < tend) load_batch(t0, kr, vr);
-        for (int tb = t0; tb < tend; tb += 8 * NP) {
-            uint4 kn[NP][VPL], vnx[NP][VPL];
-            const bool more = tb + 8 * NP < tend;
-            if (more) load_batch(tb + 8 * NP, kn, vnx);          // next batch in flight while this one is reduced
-            float sc[NP];
-            float bmax = -INFINITY;
-#pragma unroll
-            for (int pp = 0; pp < NP; ++pp) {
-                float sv = 0.f;
-#pragma unroll
-                for (int i = 0; i < VPL; ++i) {
-                    const uint4 v = kr[pp][i];
-                    float2 f2;
-                    f2 = unpack_bf16(v.x); sv += qf[i * 8 + 0] * f2.x + qf[i * 8 + 1] * f2.y;
-                    f2 = unpack_bf16(v.y); sv += qf[i * 8 + 2] * f2.x + qf[i * 8 + 3] * f2.y;
-                    f2 = unpack_bf16(v.z); sv += qf[i * 8 + 4] * f2.x + qf[i * 8 + 5] * f2.y;
-                    f2 = unpack_bf16(v.w); sv += qf[i * 8 + 6] * f2.x + qf[i * 8 + 7] * f2.y;
+                        for (int i = 0; i < VPL; ++i) {
+                            const uint4 v = lds128(a + i * 16);
+                            float2 f2;
+                            f2 = unpack_bf16(v.x); sv += qf[i * 8 + 0] * f2.x + qf[i * 8 + 1] * f2.y;
+                            f2 = unpack_bf16(v.y); sv += qf[i * 8 + 2] * f2.x + qf[i * 8 + 3] * f2.y;
+                            f2 = unpack_bf16(v.z); sv += qf[i * 8 + 4] * f2.x + qf[i * 8 + 5] * f2.y;
+                            f2 = unpack_bf16(v.w); sv += qf[i * 8 + 6] * f2.x + qf[i * 8 + 7] * f2.y;
+                        }
+                        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                        sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                        sv = valid ? sv * scale : -INFINITY;
+                        sc[pp] = sv;
+                        bmax = fmaxf(bmax, sv);
+                    }
                 }
-                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-                sv = (tb + pp * 8 + tg < tend) ? sv * scale : -INFINITY;
-                sc[pp] = sv;
-                bmax = fmaxf(bmax, sv);
-            }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
+                ++cnt;
 #pragma unroll
-            for (int off = 4; off < 32; off <<= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
-            const float m_new = fmaxf(m_run, bmax);
-            const float corr = __expf(m_run - m_new);
-            l_run *= corr;
+                for (int off = 4; off < 32; off <<= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
+                const float m_new = fmaxf(m_run, bmax);            // finite: n >= 1
+                const float corr = __expf(m_run - m_new);
+                l_run *= corr;
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) o[i] *= corr;
+                for (int i = 0; i < EPL; ++i) o[i] *= corr;
+                slot = cnt % MG_SLOTS; par = (cnt / MG_SLOTS) & 1;
+                ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+                base = ring_w + slot * MG_SLOT_BYTES;
 #pragma unroll
-            for (int pp = 0; pp < NP; ++pp) {
-                const float p = bf16r(__expf(sc[pp] - m_new));
-                l_run += p;
+                for (int pp = 0; pp < NPASS; ++pp) {
+                    if (pp * 8 < n) {
+                        const int r = pp * 8 + tg;
+                        const uint32_t a = base + (r < n ? r : 0) * ROWB;
+                        const float p = bf16r(__expf(sc[pp] - m_new));      // 0 for the padding rows (sc = -inf)
+                        l_run += p;
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) {
-                    const uint4 v = vr[pp][i];
-                    float2 f2;
-                    f2 = unpack_bf16(v.x); o[i * 8 + 0] += p * f2.x; o[i * 8 + 1] += p * f2.y;
-                    f2 = unpack_bf16(v.y); o[i * 8 + 2] += p * f2.x; o[i * 8 + 3] += p * f2.y;
-                    f2 = unpack_bf16(v.z); o[i * 8 + 4] += p * f2.x; o[i * 8 + 5] += p * f2.y;
-                    f2 = unpack_bf16(v.w); o[i * 8 + 6] += p * f2.x; o[i * 8 + 7] += p * f2.y;
+                        for (int i = 0; i < VPL; ++i) {
+                            const uint4 v = lds128(a + i * 16);
+                            float2 f2;
+                            f2 = unpack_bf16(v.x); o[i * 8 + 0] += p * f2.x; o[i * 8 + 1] += p * f2.y;
+                            f2 = unpack_bf16(v.y); o[i * 8 + 2] += p * f2.x; o[i * 8 + 3] += p * f2.y;
+                            f2 = unpack_bf16(v.z); o[i * 8 + 4] += p * f2.x; o[i * 8 + 5] += p * f2.y;
+                            f2 = unpack_bf16(v.w); o[i * 8 + 6] += p * f2.x; o[i * 8 + 7] += p * f2.y;
+                        }
+                    }
                 }
-            }
-            m_run = m_new;
-            if (more) {
-#pragma unroll
-                for (int pp = 0; pp < NP; ++pp)
-#pragma unroll
-                    for (int i = 0; i < VPL; ++i) { kr[pp][i] = kn[pp][i]; vr[pp][i] = vnx[pp][i]; }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
+                ++cnt;
+                m_run = m_new;
             }
         }
         ATR(3);
@@ -679,6 +842,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
     __shared__ __align__(8) uint64_t s_full[MG_CONSUMERS * MG_SLOTS], s_empty[MG_CONSUMERS * MG_SLOTS];
     __shared__ float s_red[MG_CONSUMERS];
     __shared__ float s_rope[2 * 128];
+    __shared__ unsigned s_epoch, s_prod_ord;
     const MegaPlan& P = *plan_g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Smem S;
@@ -691,6 +855,8 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
     S.rope = s_rope;
 
     if (tid == 0) {
+        s_epoch = 0;
+        s_prod_ord = 0;
         for (int s = 0; s < MG_CONSUMERS * MG_SLOTS; ++s) {
             ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
@@ -703,11 +869,39 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
     if (warp == MG_CONSUMERS) {
         // ------------------------------------------------------------ producer: every step's weights, in order
         uint32_t pc = 0;
-        const int inflight = P.inflight;
+        const int inflight = P.inflight, inflight_cur = P.inflight_cur;
+        const int ppos0 = P.st->ctx_len;
+        const unsigned bps = 5u * P.n_layers + 2u;     // grid barriers per step (consumer side)
+        unsigned ord = 0;
         for (int stp = 0; stp < n_steps; ++stp)
             for (int i = 0; i < n_ops; ++i) {
                 const MegaOp op = P.ops[i];
-                produce_phase(op, S, pc, inflight, lane);
+                // consumer epoch (grid barriers passed) while they work on this phase: 5 phases per layer, qkv first
+                const int l = i >> 2, j = i & 3;
+                const unsigned my_epoch = (unsigned)stp * bps + 5u * l + (j == 0 ? 0u : j + 1u);
+                produce_phase(op, S, pc, inflight, inflight_cur, &s_epoch, my_epoch, lane, &s_prod_ord, ord);
+                ord += (unsigned)cta_items(op);
+                if (j == 0 && i + 1 < n_ops && !(P.ablate & 2)) {          // after qkv: this layer's K / V stream
+                    const unsigned need = stp > 0 ? (unsigned)(stp - 1) * bps + 5u * l + 2u : 0u;
+                    produce_attention<D>(P, l, ppos0 + stp, S, pc, inflight, inflight_cur, my_epoch + 1u, lane, &s_epoch, need);
+                }
+            }
+        if (lane == 0) s_prod_ord = ord;
+        return;
+    }
+    if (warp == MG_CONSUMERS + 1) {
+        // ------------------------------------------------------------ L2 prefetcher: same item order, `pf_win` items ahead
+        const int win = P.pf_win;
+        if (win <= 0) return;
+        const int ppos0 = P.st->ctx_len;
+        unsigned ord = 0;
+        for (int stp = 0; stp < n_steps; ++stp)
+            for (int i = 0; i < n_ops; ++i) {
+                const MegaOp op = P.ops[i];
+                prefetch_phase(op, &s_prod_ord, ord, win, lane);
+                ord += (unsigned)cta_items(op);
+                if ((i & 3) == 0 && i + 1 < n_ops && !(P.ablate & 2))
+                    prefetch_attention<D>(P, i >> 2, ppos0 + stp, &s_prod_ord, ord, win, lane);
             }
         return;
     }
@@ -739,37 +933,37 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             long long* occ = tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ : nullptr);
             op = P.ops[l * 4 + 1];
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
             // rope + KV append + split-KV attention
-            if (!(ablate & 2)) attention_phase<D>(P, l, pos, S, warp, lane);
+            if (!(ablate & 2)) attention_phase<D>(P, l, pos, S, cnt, warp, lane);
             tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
             // merge + o_proj + residual
             if (!(ablate & 4)) stage_x_attn(P, S, pos + 1, tid);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 8 : nullptr);
             op = P.ops[l * 4 + 2];
             prefetch_norm(op, np, tid);
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
             // norm + gate_up + SwiGLU
             if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 16 : nullptr);
             op = P.ops[l * 4 + 3];
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
             // down + residual
             if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 24 : nullptr);
             op = P.ops[l * 4 + 4];
             prefetch_norm(op, np, tid);
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
         }
         // norm + lm_head + bias + greedy pick
         stage_x_vec(op, op.x, np, S, tid, warp, lane);
         tr.mark(tid);
         gemv_items(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, ablate); tr.mark(tid);
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
         // ---- bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
         if (blockIdx.x == 0 && tid == 0) {
             DecodeState* st = P.st;
@@ -784,7 +978,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             st->attn_len = pos + 1;
             st->step = step + 1;
         }
-        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, tid, ablate);   // the next step reads cur_token
+        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate);   // the next step reads cur_token
     }
     if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 1] = (long long)globaltimer_ns();
 }
@@ -861,8 +1055,14 @@ bool decode_mega_finalize(MegaPlan* p) {
     p->ablate = ab ? atoi(ab) : 0;
     const char* env = getenv("GVL_MEGA_INFLIGHT");
     p->inflight = env ? atoi(env) : 1;
+    const char* ec = getenv("GVL_MEGA_INFLIGHT_CUR");
+    p->inflight_cur = ec ? atoi(ec) : MG_SLOTS;
+    const char* pw = getenv("GVL_MEGA_PFWIN");
+    p->pf_win = pw ? atoi(pw) : 0;                     // measured slower with the prefetcher on (profiles/r1_decode.md)
     if (p->inflight < 1) p->inflight = 1;
     if (p->inflight > MG_SLOTS) p->inflight = MG_SLOTS;
+    if (p->inflight_cur < p->inflight) p->inflight_cur = p->inflight;
+    if (p->inflight_cur > MG_SLOTS) p->inflight_cur = MG_SLOTS;
     return (size_t)MG_RING_BYTES + p->x_bytes + (size_t)items * 32 <= (size_t)MG_SMEM_LIMIT;
 }
 

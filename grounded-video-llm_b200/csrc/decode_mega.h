@@ -38,6 +38,8 @@ struct MegaPlan {
     int n_layers, dim, heads, kv_heads, head_dim, vocab, max_ctx;
     int ablate;                 // bring-up only (GVL_MEGA_ABLATE): 1 skip grid barriers, 2 skip attention, 4 skip staging, 8 skip the GEMV math
     int inflight;               // bulk copies each producer lane keeps outstanding (1..3; GVL_MEGA_INFLIGHT)
+    int inflight_cur;           // ... once the consumers have reached the phase being produced (GVL_MEGA_INFLIGHT_CUR)
+    int pf_win;                 // L2 prefetch distance ahead of the ring producer, in 8 KB items per CTA (0 = off; GVL_MEGA_PFWIN)
     int x_bytes;                // activation staging area (also the attention-phase scratch)
     int part_items;             // capacity of the per-item partial-sum buffer (8 floats per item)
     int att_maxp;               // split-KV partials per head in att_ws

@@ -164,7 +164,8 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
     cudaMemset(lm->da_ws, 0, decode_attention_workspace(w->heads, w->head_dim, w->max_ctx));
     {
         const char* env = getenv("GVL_DECODE_MEGA");
-        lm->use_mega = (env && env[0] == '1') && w->n_layers <= MEGA_MAX_LAYERS;
+        // single-kernel decode step is the default (measured faster than the per-op chain); GVL_DECODE_MEGA=0 selects the chain
+        lm->use_mega = !(env && env[0] == '0') && w->n_layers <= MEGA_MAX_LAYERS;
         if (lm->use_mega) {
             MegaPlan* hp = new MegaPlan();
             memset(hp, 0, sizeof(MegaPlan));
