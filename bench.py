@@ -254,6 +254,20 @@ def run_gvl_arm(args):
     lib.gvl_profile_enable(0)
     for lmh in m.language_model._lms.values():
         lib.gvl_lm_set_graph(lmh, 1)
+    # ---- decode roofline: clean (profiling off) prefill vs prefill + 16-token generate on the same embeddings; the
+    # difference is the 15 decode steps of the single-kernel decode path (one launch runs all steps of a generate call)
+    dv = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
+    torch.cuda.synchronize()
+    dv[0].record()
+    m.language_model.prefill(emb[0], n_new=DECODE_TOKENS)
+    dv[1].record()
+    m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
+    dv[2].record()
+    torch.cuda.synchronize()
+    dec_steps = DECODE_TOKENS - 1                                     # the first token comes out of the prefill
+    dec_step_ms = (dv[1].elapsed_time(dv[2]) - dv[0].elapsed_time(dv[1])) / dec_steps
+    dec_bytes = DECODE_BYTES_WEIGHTS + (emb.shape[1] + dec_steps / 2.0) * KV_BYTES_PER_CTX_TOKEN
     fam = {}
     for kind, name in ((0, "gemm"), (1, "attn"), (2, "gemv")):
         ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -279,10 +293,14 @@ def run_gvl_arm(args):
             "prefill_tflops_achieved": prefill_flops / prefill_s / 1e12,
             "prefill_frac_of_tensor_peak": prefill_flops / prefill_s / 1e12 / pk["tf_sustained"],
             "attention": {"ms": a_ms, "tflops": a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None, "launches": a_n,
-                          "kernel": "gvl::attn_fwd_kernel"},
-            "decode_gemv": {"ms": v_ms, "gbs": v_by / (v_ms * 1e-3) / 1e9 if v_ms > 0 else None, "launches": v_n,
-                            "frac_of_hbm_peak": (v_by / (v_ms * 1e-3) / 1e9 / pk["hbm"]) if v_ms > 0 else None,
-                            "kernel": "gvl::gemv_kernel"},
+                          "kernel": "gvl::attn_tc2_kernel (tcgen05; attn_tc_kernel for single-tile shapes)"},
+            "decode": {"bound": "hbm", "ms_per_step": dec_step_ms, "bytes_per_step": dec_bytes,
+                       "achieved_gbs": dec_bytes / (dec_step_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
+                       "frac": dec_bytes / (dec_step_ms * 1e-3) / 1e9 / pk["hbm"],
+                       "kernel": "gvl::decode_mega_kernel<96> (one persistent launch per generate call; GVL_DECODE_MEGA=0: per-op chain)"
+                                 if os.environ.get("GVL_DECODE_MEGA", "1") != "0" else "per-op chain: gemv3_kernel + decode_attn_kernel (CUDA graph)",
+                       "how": "CUDA events: (prefill + %d-token generate) - prefill, / %d steps; bytes = 7.447 GB weights + ctx x 393 KB K/V" % (DECODE_TOKENS, dec_steps)},
+            "gemv_launches_profiled": {"ms": v_ms, "launches": v_n},
             "peaks": pk,
         }
     cpu = None

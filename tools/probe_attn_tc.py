@@ -20,6 +20,11 @@ CASES = {
     "d128_gqa_causal": (1, 8, 2, 300, 300, 128, True, False, 0),
     "d128_two_tiles": (1, 2, 2, 256, 256, 128, False, False, 0),
     "d96_q1": (1, 4, 4, 1, 130, 96, True, False, 0),
+    "d96_iv2_b12": (12, 16, 16, 2049, 2049, 96, False, False, 88),
+    "d64_clip_b12": (12, 16, 16, 577, 577, 64, False, True, 0),
+    "d128_llama_long": (1, 32, 8, 2380, 2380, 128, True, False, 0),
+    "d96_odd_sub": (1, 4, 4, 700, 700, 96, False, False, 0),
+    "d96_causal_offset": (1, 4, 4, 300, 1000, 96, True, False, 0),
 }
 
 
