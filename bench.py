@@ -178,6 +178,8 @@ def run_gvl_arm(args):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout; rank 0 must print exactly ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     lib = _lib.load()
     B = world * args.clips_per_gpu
@@ -228,6 +230,32 @@ def run_gvl_arm(args):
     for _ in range(2):
         one_step(host, True)
     e2e_ms = timed(host, True, args.steps)
+    # ---- e2e from RAW frames (SURVEY 8d synthetic clip: uint8 [96,3,336,336], seed 1234): H2D of the uint8 clip, GPU
+    # frame_transform (bit-exact Pillow bicubic 336 -> 224 + normalisation, csrc/preprocess.cu), then the same generate call
+    from gvl import preprocess
+    raw_host = torch.randint(0, 256, (B, 96, 3, 336, 336), dtype=torch.uint8, generator=torch.Generator().manual_seed(1234)).pin_memory()
+
+    def raw_step():
+        raw = raw_host.to(dev, non_blocking=True)
+        px = [preprocess.create_pixel_inputs(raw[b], 96, 12) for b in range(B)]
+        smp = dict(host)
+        smp["spatial_pixel_values"] = torch.cat([p_["spatial_pixel_values"] for p_ in px])
+        smp["temporal_pixel_values"] = torch.cat([p_["temporal_pixel_values"] for p_ in px])
+        return [t.cpu() for t in m.generate(smp, max_new_tokens=DECODE_TOKENS)]
+
+    for _ in range(2):
+        raw_step()
+    rv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a_, b_ in rv:
+        a_.record()
+        raw_step()
+        b_.record()
+    barrier()
+    raw_t = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in rv)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(raw_t, op=dist.ReduceOp.MAX)
+    raw_ms = float(raw_t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline pass: per-kernel-family CUDA events on the launching stream, one extra step, graph replay off
@@ -301,6 +329,10 @@ def run_gvl_arm(args):
                                  if os.environ.get("GVL_DECODE_MEGA", "1") != "0" else "per-op chain: gemv3_kernel + decode_attn_kernel (CUDA graph)",
                        "how": "CUDA events: (prefill + %d-token generate) - prefill, / %d steps; bytes = 7.447 GB weights + ctx x 393 KB K/V" % (DECODE_TOKENS, dec_steps)},
             "gemv_launches_profiled": {"ms": v_ms, "launches": v_n},
+            "e2e_from_raw_frames": {"value": B * args.steps / (raw_ms * 1e-3), "unit": UNIT, "ms_per_step": raw_ms / args.steps,
+                                    "h2d_bytes_per_step": B * 96 * 3 * 336 * 336 + B * T_TEXT * 8,
+                                    "what": "uint8 clip [96,3,336,336] in pinned host memory -> H2D -> GPU frame_transform (Pillow-bicubic "
+                                            "bit-exact resize 336->224, key-frame selection, normalisation) -> generate -> tokens to host"},
             "peaks": pk,
         }
     cpu = None

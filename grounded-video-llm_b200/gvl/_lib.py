@@ -103,6 +103,9 @@ _SIGS = {
     "gvl_lm_first_token": (c_vp, [c_vp]),
     "gvl_lm_set_graph": (c_i, [c_vp, c_i]),
     "gvl_lm_mega_trace": (c_i, [c_vp, c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
+    "gvl_frame_transform_workspace": (ctypes.c_size_t, [c_i, c_i, c_i, c_i, c_i]),
+    "gvl_frame_transform": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, ctypes.POINTER(ctypes.c_float),
+                                  ctypes.POINTER(ctypes.c_float), c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "gvl_profile_enable": (c_i, [c_i]),
     "gvl_profile_collect": (c_i, [c_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(c_ll)]),

@@ -99,6 +99,18 @@ int gvl_rope_qkv_cache(const void* qkv, void* q_out, void* k_cache, void* v_cach
                        const void* sin_bf16, const int* positions, int tokens, int heads, int kv_heads,
                        int head_dim, int pos0, int max_ctx, void* stream);
 
+/* ------------------------------------------------------------------ frame preprocessing
+ * frame_transform (mm_utils/utils.py:153-183; call sites inference.py:69-88): ToPILImage -> Resize(size, BICUBIC) ->
+ * CenterCrop(size) -> ToTensor -> Normalize on uint8 frames [n,3,h,w] -> float32 [n,3,size,size], bit-exact with
+ * Pillow's 8-bit bicubic resampling (fixed-point two-pass convolution) and torchvision's float32 arithmetic.
+ * new_h / new_w = torchvision's shortest-edge resize result, crop_top / crop_left = its center-crop offsets (both are
+ * computed by the caller with the reference's exact integer rules, gvl/preprocess.py). mean3 / std3 are HOST pointers.
+ * workspace: gvl_frame_transform_workspace bytes of device memory (the 8-bit intermediate image; 0 when w == new_w). */
+size_t gvl_frame_transform_workspace(int n, int h, int w, int new_h, int new_w);
+int gvl_frame_transform(const unsigned char* frames, int n, int h, int w, int new_h, int new_w, int crop_top,
+                        int crop_left, int size, const float* mean3, const float* std3, float* out, void* workspace,
+                        size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ decode-side operators
  * y[M,N] = x[M,K] @ W[N,K]^T for M <= 8 (weight-streaming, HBM-bound). Optional fused input RMSNorm
  * (norm_w != NULL), bias, SwiGLU (same interleaved W as gvl_gemm_bf16), bf16 residual, fp32 output. */
