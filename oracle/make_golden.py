@@ -306,6 +306,24 @@ def gold_host_logic():
         json.dump(out, fh, indent=1)
     print("wrote host_logic.json")
 
+def golden_ingest(out_dir):
+    """the reference's own interpolate_pos_embed_internvideo2_new (internvideo2.py:260-320) on a small synthetic
+    checkpoint (orig_t_size 4 -> 8 frames, 4 x 4 spatial grid) -> tests/golden/ingest_pos_embed.npz."""
+    import types
+    R.import_models()
+    iv2 = R._mods["iv2"]
+    g = torch.Generator().manual_seed(77)
+    c, hw = 24, 16
+    ckpt = {"pos_embed": torch.randn(1, 1 + 4 * hw, c, generator=g), "clip_pos_embed": torch.randn(1, 1 + 4 * hw, c, generator=g),
+            "img_pos_embed": torch.randn(1, 1 + hw, c, generator=g)}
+    src = {k: v.clone() for k, v in ckpt.items()}
+    model = types.SimpleNamespace(patch_embed=types.SimpleNamespace(num_patches=8 * hw), pos_embed=torch.zeros(1, 1 + 8 * hw, c),
+                                  num_frames=8, tubelet_size=1)
+    iv2.interpolate_pos_embed_internvideo2_new(ckpt, model, orig_t_size=4)
+    np.savez_compressed(os.path.join(out_dir, "ingest_pos_embed.npz"), **{"in_" + k: v.numpy() for k, v in src.items()},
+                        **{"out_" + k: v.numpy() for k, v in ckpt.items()})
+    print("ingest_pos_embed: pos_embed", tuple(ckpt["pos_embed"].shape))
+
 
 def main():
     if not R.available():
@@ -318,7 +336,9 @@ def main():
     gold_llama(mods)
     gold_index_maps()
     gold_host_logic()
+    golden_ingest(GOLD)
 
 
 if __name__ == "__main__":
     main()
+
