@@ -390,6 +390,15 @@ int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas
 
 const long long* gvl_lm_first_token(gvl_lm* lm) { return lm ? lm->first_tok : nullptr; }
 
+int gvl_lm_set_next_token(gvl_lm* lm, const long long* token_dev, void* stream) {
+    if (!lm || !token_dev) return GVL_ERR_ARG;
+    cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+    // decode steps run on the object's own stream and fence themselves against the caller's with events (gvl_lm_decode), so a
+    // copy enqueued on the caller's stream is ordered after the previous step and before the next one
+    CU(cudaMemcpyAsync(&lm->st->cur_token, token_dev, sizeof(long long), cudaMemcpyDeviceToDevice, caller));
+    return GVL_OK;
+}
+
 int gvl_lm_set_graph(gvl_lm* lm, int on) {
     if (!lm) return GVL_ERR_ARG;
     lm->use_graph = on != 0;

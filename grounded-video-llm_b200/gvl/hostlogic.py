@@ -124,3 +124,25 @@ def plain_rope_tables(max_ctx, head_dim, base, bf16_matmul_quirk=False):
     freqs = pos[:, None] * inv_freq[None, :]
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
+
+
+def warp_logits(scores, temperature=None, top_k=50, top_p=None, min_tokens_to_keep=1):
+    """HF logits warpers in GenerationMixin._get_logits_warper order (third-party transformers==4.40.1, used by the reference's
+    `.generate(do_sample=True, temperature=0.2, top_p=None)`, inference.py:170-176): TemperatureLogitsWarper (scores / T),
+    TopKLogitsWarper (keep the k largest; ties with the k-th value survive), TopPLogitsWarper (drop the ascending-sorted tail
+    whose cumulative probability is <= 1 - top_p, always keep the last `min_tokens_to_keep`). scores: float [B, V]."""
+    import torch
+    if temperature is not None and temperature != 1.0:
+        scores = scores / temperature
+    if top_k is not None and top_k > 0:
+        k = min(max(int(top_k), min_tokens_to_keep), scores.shape[-1])
+        kth = torch.topk(scores, k)[0][..., -1, None]
+        scores = scores.masked_fill(scores < kth, -float("inf"))
+    if top_p is not None and top_p < 1.0:
+        sorted_logits, sorted_indices = torch.sort(scores, descending=False)
+        cumulative = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        remove_sorted = cumulative <= (1 - top_p)
+        remove_sorted[..., -min_tokens_to_keep:] = False
+        remove = remove_sorted.scatter(1, sorted_indices, remove_sorted)
+        scores = scores.masked_fill(remove, -float("inf"))
+    return scores

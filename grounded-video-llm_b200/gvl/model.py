@@ -228,13 +228,62 @@ class CausalLM:
             self._lmh = (w, b)
         return self._lmh
 
+    def _sample(self, inputs_embeds, attention_mask, eos_token_id, pad_token_id, max_new_tokens, temperature, top_k, top_p,
+                generator, return_logits):
+        """HF sampling loop (GenerationMixin._sample, transformers==4.40.1; call site llava_next_video.py:655-661 with
+        inference.py's do_sample=True, temperature=0.2): per step logits -> warpers -> softmax -> multinomial. The logits
+        come from the library one step at a time; the pick happens on the device with torch (no host synchronisation), is
+        handed back with gvl_lm_set_next_token, and finished rows emit pad_token_id like HF's unfinished_sequences mask."""
+        lib = _lib.load()
+        B = inputs_embeds.shape[0]
+        outs, logs = [], []
+        for b in range(B):
+            emb = inputs_embeds[b]
+            if attention_mask is not None:
+                emb = emb[attention_mask[b].to(emb.device).bool()]
+            logits, _ = self.prefill(emb, n_new=max_new_tokens)
+            lm, _S = self._active
+            toks = torch.empty((max_new_tokens,), dtype=torch.int64, device=self.device)
+            lg = torch.empty((max_new_tokens, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            step_logits = torch.empty((1, self.vocab), dtype=torch.float32, device=self.device)
+            scratch = torch.empty((1,), dtype=torch.int64, device=self.device)
+            unfinished = torch.ones((), dtype=torch.int64, device=self.device)
+            for t in range(max_new_tokens):
+                if return_logits:
+                    lg[t].copy_(logits.reshape(-1))
+                scores = hostlogic.warp_logits(logits.reshape(1, -1), temperature, top_k, top_p)
+                nxt = torch.multinomial(torch.softmax(scores, dim=-1), num_samples=1, generator=generator).reshape(())
+                nxt = nxt * unfinished + int(pad_token_id) * (1 - unfinished)
+                toks[t] = nxt
+                if eos_token_id is not None:
+                    unfinished = unfinished * (nxt != int(eos_token_id)).to(torch.int64)
+                if t + 1 < max_new_tokens:
+                    rc = lib.gvl_lm_set_next_token(lm, ctypes.c_void_p(toks[t:t + 1].data_ptr()), _stream())
+                    _lib.check(rc, "gvl_lm_set_next_token")
+                    rc = lib.gvl_lm_decode(lm, 1, ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(step_logits.data_ptr()),
+                                           -1, int(pad_token_id), _stream())
+                    _lib.check(rc, "gvl_lm_decode")
+                    logits = step_logits
+            outs.append(toks)
+            logs.append(lg)
+        out = torch.stack(outs, dim=0)
+        return (out, torch.stack(logs, dim=0)) if return_logits else out
+
     def generate(self, inputs_embeds=None, attention_mask=None, eos_token_id=None, pad_token_id=0, do_sample=False,
-                 num_beams=1, max_new_tokens=16, temperature=None, top_p=None, return_logits=False, **unused):
-        """Greedy generate for a batch of left-padded sequences (each row is compacted with its attention_mask and run
+                 num_beams=1, max_new_tokens=16, temperature=None, top_p=None, top_k=50, generator=None, return_logits=False,
+                 **unused):
+        """generate for a batch of left-padded sequences (each row is compacted with its attention_mask and run
         as an unpadded sequence: identical to the reference's varlen path because padding carries mask 0 and
-        position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, max_new_tokens]."""
-        if do_sample or num_beams != 1:
-            raise NotImplementedError("gvl implements the greedy parity mode (do_sample=False, num_beams=1)")
+        position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, max_new_tokens].
+        do_sample=False: greedy, all steps inside the library (one launch). do_sample=True: HF sampling (temperature, top_k
+        -- HF's GenerationConfig default 50 --, top_p, multinomial), one library step per token."""
+        if num_beams != 1:
+            raise NotImplementedError("beam search is not on the reference's inference path (num_beams=1, inference.py:172)")
+        if inputs_embeds.dim() == 2:
+            inputs_embeds = inputs_embeds[None]
+        if do_sample:
+            return self._sample(inputs_embeds, attention_mask, eos_token_id, pad_token_id, max_new_tokens, temperature, top_k,
+                                top_p, generator, return_logits)
         lib = _lib.load()
         if inputs_embeds.dim() == 2:
             inputs_embeds = inputs_embeds[None]

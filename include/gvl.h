@@ -234,6 +234,10 @@ int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas
 
 /* first generated token (argmax of the prefill logits), device int64 */
 const long long* gvl_lm_first_token(gvl_lm* lm);
+/* Sampling decode (HF generate with do_sample=True, llava_next_video.py:655-661 / inference.py:170-176): the caller picks the
+ * next token itself from the logits of the previous step (temperature / top-k / top-p / multinomial happen outside, on the
+ * device) and hands it back before the next gvl_lm_decode(lm, 1, ...) call. token_dev: ONE device int64. */
+int gvl_lm_set_next_token(gvl_lm* lm, const long long* token_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -303,6 +303,40 @@ def test_lm_decode_single_kernel_ring_fed_kv(gvl, arch, heads, kvh, hd, ctx, mon
     lm2.close()
 
 
+@pytest.mark.parametrize("mega", ["1", "0"])
+def test_sampling_decode_hf_semantics(gvl, mega, monkeypatch):
+    """do_sample=True (the reference CLI default, inference.py:45-49): top_k=1 must reproduce the greedy chain step by step
+    (same logits through the one-step-per-token path), a fixed generator reproduces itself, finished rows emit pad, and the
+    sampled tokens always lie in the top-k set of the logits that were returned for that step."""
+    monkeypatch.setenv("GVL_DECODE_MEGA", mega)
+    P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=2, vocab=1000, seed=21, std=0.05)
+    rope = O.phi35_rope_cfg(64)
+    lm = gvl.model.CausalLM(P, "phi3", 4, 4, 64, 1e-5, rope, max_ctx=512)
+    emb = (torch.randn(150, 256, generator=torch.Generator().manual_seed(3)) * 0.5).cuda()
+    greedy, lg_g = lm.generate(inputs_embeds=emb[None], max_new_tokens=6, return_logits=True)
+    top1, lg_1 = lm.generate(inputs_embeds=emb[None], max_new_tokens=6, do_sample=True, top_k=1, temperature=0.2, return_logits=True)
+    assert top1.tolist() == greedy.tolist()
+    _cmp(lg_1[0], lg_g[0], atol=1e-6)                     # same kernels, same inputs: the per-token path changes nothing
+    g1 = torch.Generator(device="cuda").manual_seed(11)
+    g2 = torch.Generator(device="cuda").manual_seed(11)
+    a, lg_a = lm.generate(inputs_embeds=emb[None], max_new_tokens=8, do_sample=True, temperature=1.5, top_k=5, generator=g1,
+                          return_logits=True)
+    b = lm.generate(inputs_embeds=emb[None], max_new_tokens=8, do_sample=True, temperature=1.5, top_k=5, generator=g2)
+    assert a.tolist() == b.tolist()
+    for t in range(8):
+        assert int(a[0, t]) in torch.topk(lg_a[0, t], 5).indices.tolist()
+    assert len(set(a[0].tolist())) > 1 or a.tolist() != greedy.tolist()[:8]
+    eos = int(a[0, 2])
+    first = a[0].tolist().index(eos)
+    g3 = torch.Generator(device="cuda").manual_seed(11)
+    c = lm.generate(inputs_embeds=emb[None], max_new_tokens=8, do_sample=True, temperature=1.5, top_k=5, generator=g3,
+                    eos_token_id=eos, pad_token_id=7)
+    assert c[0, :first + 1].tolist() == a[0, :first + 1].tolist() and all(x == 7 for x in c[0, first + 1:].tolist())
+    with pytest.raises(NotImplementedError):
+        lm.generate(inputs_embeds=emb[None], max_new_tokens=2, num_beams=2)
+    lm.close()
+
+
 def test_eos_padding_semantics(gvl):
     P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=1, vocab=300, seed=11,
                          std=0.05)

@@ -98,3 +98,23 @@ def test_gate_up_interleave_and_clip_pack_cpu():
     assert pk.struct.kpad == 640 and pk.struct.n_patch == 16 and pk.struct.n_layers == 1
     with pytest.raises(ValueError):
         weights.pack_clip(O.make_clip_params(dim=96, heads=4, ffn=128, layers=1, image=56), 4, 1, device="cpu", image=56)
+
+
+def test_warp_logits_matches_transformers_warpers():
+    """hostlogic.warp_logits vs the third-party library the reference calls (transformers LogitsWarper classes)."""
+    lp = pytest.importorskip("transformers.generation.logits_process")
+    g = torch.Generator().manual_seed(5)
+    scores = torch.randn(3, 500, generator=g) * 3
+    scores[0, 10] = scores[0, 11]                                   # a tie
+    ids = torch.zeros(3, 1, dtype=torch.long)
+    for temperature, top_k, top_p in [(0.2, 50, None), (1.0, 50, 0.9), (0.7, 0, 0.5), (0.2, 5, 0.95), (None, 1, None)]:
+        ref = scores.clone()
+        if temperature is not None and temperature != 1.0:
+            ref = lp.TemperatureLogitsWarper(temperature)(ids, ref)
+        if top_k:
+            ref = lp.TopKLogitsWarper(top_k=top_k)(ids, ref)
+        if top_p is not None:
+            ref = lp.TopPLogitsWarper(top_p=top_p)(ids, ref)
+        got = H.warp_logits(scores.clone(), temperature, top_k, top_p)
+        assert torch.equal(torch.isinf(got), torch.isinf(ref)), (temperature, top_k, top_p)
+        assert torch.equal(torch.nan_to_num(got, neginf=0.0), torch.nan_to_num(ref, neginf=0.0))
