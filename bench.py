@@ -284,7 +284,7 @@ def run_gvl_arm(args):
         lib.gvl_lm_set_graph(lmh, 1)
     # ---- decode roofline: clean (profiling off) prefill vs prefill + 16-token generate on the same embeddings; the
     # difference is the 15 decode steps of the single-kernel decode path (one launch runs all steps of a generate call)
-    dv = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    dv = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
     torch.cuda.synchronize()
     dv[0].record()
@@ -292,7 +292,15 @@ def run_gvl_arm(args):
     dv[1].record()
     m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
     dv[2].record()
+    # clean prefill-side timing (the per-launch events of the family pass above cost ~10 % of the prefill)
+    feats2 = m.encode_images(resident)
+    dv[3].record()
+    emb2, _, _ = m.prepare_multimodal_inputs(ids[mine], None, mask[mine], feats2[mine], ["v"] * len(mine))
+    for i in range(len(mine)):
+        m.language_model.prefill(emb2[i], n_new=DECODE_TOKENS)
+    dv[4].record()
     torch.cuda.synchronize()
+    clean_enc_ms, clean_pre_ms = dv[2].elapsed_time(dv[3]), dv[3].elapsed_time(dv[4])
     dec_steps = DECODE_TOKENS - 1                                     # the first token comes out of the prefill
     dec_step_ms = (dv[1].elapsed_time(dv[2]) - dv[0].elapsed_time(dv[1])) / dec_steps
     dec_bytes = DECODE_BYTES_WEIGHTS + (emb.shape[1] + dec_steps / 2.0) * KV_BYTES_PER_CTX_TOKEN
@@ -308,16 +316,21 @@ def run_gvl_arm(args):
         v_ms, v_by, v_n = fam["gemv"]
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"kernel": "gvl::gemm_bf16_tcgen05_kernel (all epilogue variants)", "bound": "tensor", "achieved": ach,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                # dram__bytes_read + dram__bytes_write of ONE captured launch of this family (InternVideo2 fc1, 24588x6144x1408,
+                # profiles/r1_gemm_r1_ncu_metrics.csv; algorithmic 388 MB): constant from the committed ncu capture, not measured live
+                "traffic": 336.0e6, "traffic_launch": "IV2 fc1 24588x6144x1408 (ncu --set full, profiles/r1_gemm.md)",
                 "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                 "share_of_step_ms": g_ms}
         enc_ms, pre_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
         per_rank_clips = len(mine)
-        prefill_s = (enc_ms + pre_ms) * 1e-3
+        prefill_s = (clean_enc_ms + clean_pre_ms) * 1e-3
         units_here = 12 * B / world
         prefill_flops = units_here * (FLOPS_CLIP + FLOPS_IV2 + FLOPS_PROJ) / 12 + per_rank_clips * FLOPS_LM
         extra = {
             "stage_ms_profiled": {"encode_images": enc_ms, "splice+prefill": pre_ms, "prefill+%d_decode" % DECODE_TOKENS: dec_ms},
+            "stage_ms": {"encode_images": clean_enc_ms, "splice+prefill": clean_pre_ms, "decode_step": dec_step_ms,
+                         "note": "CUDA events without the per-launch profiling events; prefill_tflops_achieved uses these"},
             "prefill_tflops_achieved": prefill_flops / prefill_s / 1e12,
             "prefill_frac_of_tensor_peak": prefill_flops / prefill_s / 1e12 / pk["tf_sustained"],
             "attention": {"ms": a_ms, "tflops": a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else None, "launches": a_n,
@@ -325,6 +338,7 @@ def run_gvl_arm(args):
             "decode": {"bound": "hbm", "ms_per_step": dec_step_ms, "bytes_per_step": dec_bytes,
                        "achieved_gbs": dec_bytes / (dec_step_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
                        "frac": dec_bytes / (dec_step_ms * 1e-3) / 1e9 / pk["hbm"],
+                       "traffic_bytes_per_step_ncu": 8.90e9,   # dram__bytes_read of one captured launch / its 8 steps (profiles/r1_decode_mega_ncu_metrics.csv)
                        "kernel": "gvl::decode_mega_kernel<96> (one persistent launch per generate call; GVL_DECODE_MEGA=0: per-op chain)"
                                  if os.environ.get("GVL_DECODE_MEGA", "1") != "0" else "per-op chain: gemv3_kernel + decode_attn_kernel (CUDA graph)",
                        "how": "CUDA events: (prefill + %d-token generate) - prefill, / %d steps; bytes = 7.447 GB weights + ctx x 393 KB K/V" % (DECODE_TOKENS, dec_steps)},
