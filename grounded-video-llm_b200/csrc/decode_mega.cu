@@ -113,18 +113,21 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 consumer threads
 
 // consumers-only grid barrier
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid, volatile unsigned* cta_epoch,
-                                             int ablate = 0) {
+// `epoch` counts phase boundaries (published for the producer warp), `bars` counts the REAL grid barriers among them (in the
+// flags-in-data mode most boundaries are phase_end() below)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned& bars, int tid,
+                                             volatile unsigned* cta_epoch, int ablate = 0) {
     cbar();
     ++epoch;
     if (ablate & 1) {                                // timing ablation only (results are wrong)
         if (tid == 0) *cta_epoch = epoch;
         return;
     }
+    ++bars;
     if (tid == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        const unsigned target = epoch * gridDim.x;
+        const unsigned target = bars * gridDim.x;
         if (ld_acquire_u32(counter) < target) {
             const long long t0 = clock64();
             while (ld_acquire_u32(counter) < target) {
@@ -138,6 +141,56 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
         *cta_epoch = epoch;                          // the producer warp gates its K / V stream on this (produce_attention)
     }
     cbar();
+}
+// flags-in-data mode: a phase boundary without a grid barrier (the next phase polls its inputs)
+__device__ __forceinline__ void phase_end(unsigned& epoch, int tid, volatile unsigned* cta_epoch) {
+    cbar();
+    ++epoch;
+    if (tid == 0) {
+        __threadfence_block();
+        *cta_epoch = epoch;
+    }
+}
+
+// ------------------------------------------------------------------ flags-in-data packets
+__device__ __forceinline__ uint4 ld_poll4(const void* p) {          // L1-bypassing, never hoisted out of a polling loop
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint2 ld_poll2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_packet2(uint2* p, uint32_t data, uint32_t flag) {
+    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void st_packet4(uint4* p, float a, float b, float c, uint32_t flag) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+                 "r"(__float_as_uint(c)), "r"(flag) : "memory");
+}
+struct PollGuard {                                                  // a producer died or the phase ids are out of step: trap, never hang
+    long long t0;
+    __device__ __forceinline__ PollGuard() : t0(0) {}
+    __device__ __forceinline__ void spin(const char* what, unsigned want, unsigned got) {
+        if (t0 == 0) { t0 = clock64(); __nanosleep(200); return; }
+        __nanosleep(400);                                           // 38k threads poll: keep the request rate off the weight stream
+        if (clock64() - t0 > 4000000000LL) {
+            printf("gvl: decode_mega %s poll timeout block %d thread %d want %u got %u\n", what, blockIdx.x, threadIdx.x, want, got);
+            __trap();
+        }
+    }
+};
+// 4 consecutive elements (two packets) of an LL vector, polled until both carry `flag`; returns the 4 bf16 as (lo pair, hi pair)
+__device__ __forceinline__ uint2 poll_vec4(const uint2* v, int idx4, unsigned flag, const char* what) {
+    PollGuard g;
+    uint4 r = ld_poll4(v + (size_t)idx4 * 2);
+    while (r.y != flag || r.w != flag) {
+        g.spin(what, flag, r.y != flag ? r.y : r.w);
+        r = ld_poll4(v + (size_t)idx4 * 2);
+    }
+    return make_uint2(r.x, r.z);
 }
 
 // optional per-CTA phase trace (clock64 at: x staged / work done / barrier passed), MegaPlan::trace != nullptr
@@ -246,6 +299,123 @@ __device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat1
     cbar();
 }
 
+// ------------------------------------------------------------------ x staging from {2 x bf16, flag} packets (+ RMSNorm): the poll IS the load
+__device__ __noinline__ void stage_x_ll(const MegaOp& op, unsigned flag, const Smem& S, int tid, int warp, int lane) {
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
+    const int nq = op.K / 4;                                       // 4 elements per thread-load; K <= 8192 -> <= 8 per thread
+    uint2 nw[8];
+    if (op.norm_w != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (tid + u * 256 < nq) nw[u] = __ldg(reinterpret_cast<const uint2*>(op.norm_w) + tid + u * 256);
+    }
+    // 38k threads re-polling every packet they need put more requests on the L2 than the weight stream itself: only warp 0
+    // waits, on 32 sentinel packets spread over the vector (32 different producer CTAs), everybody else sleeps at the CTA barrier;
+    // afterwards every thread loads its packets once, still verifying the flags (a late packet is re-polled individually)
+    if (warp == 0) {
+        PollGuard g;
+        const uint2* sp = op.x_ll + (size_t)(lane * (nq / 32)) * 2;
+        uint4 r = ld_poll4(sp);
+        while (!__all_sync(0xffffffffu, r.y == flag && r.w == flag)) {
+            g.spin("x sentinel", flag, r.y);
+            r = ld_poll4(sp);
+        }
+    }
+    cbar();
+    uint2 xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (tid + u * 256 < nq) xv[u] = poll_vec4(op.x_ll, tid + u * 256, flag, "x");
+    if (op.norm_w == nullptr) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (tid + u * 256 < nq) reinterpret_cast<uint2*>(sx)[tid + u * 256] = xv[u];
+        cbar();
+        return;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (tid + u * 256 < nq) {
+            float2 f;
+            f = unpack_bf16(xv[u].x); ss += f.x * f.x + f.y * f.y;
+            f = unpack_bf16(xv[u].y); ss += f.x * f.x + f.y * f.y;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) S.red[warp] = ss;
+    cbar();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
+    const float rstd = rsqrtf(t / op.K + op.eps);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (tid + u * 256 < nq) {
+            float2 f, g;
+            uint2 o;
+            f = unpack_bf16(xv[u].x); g = unpack_bf16(nw[u].x); o.x = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+            f = unpack_bf16(xv[u].y); g = unpack_bf16(nw[u].y); o.y = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
+            reinterpret_cast<uint2*>(sx)[tid + u * 256] = o;
+        }
+    cbar();
+}
+
+// merge of the split-KV partials from {3 floats, flag} packets: task (head, l) owns dims l, l + 32, l + 64 of that head
+__device__ __noinline__ void stage_x_attn_ll(const MegaPlan& P, unsigned flag, const Smem& S, int ctx, int tid) {
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
+    const int D = P.head_dim, H = P.heads, maxp = P.att_maxp;
+    const int Lc = att_warp_len(ctx, H, gridDim.x) * MG_CONSUMERS;
+    if (tid < 32) {                                                 // sentinels: the (m, l) packet of every partial, one head per lane
+        for (int h = tid; h < H; h += 32) {
+            const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+            for (int s = 0; s <= c1 - c0; ++s) {
+                PollGuard g;
+                const uint4* sp = P.att_ll + ((size_t)h * maxp + s) * 33 + 32;
+                uint4 r = ld_poll4(sp);
+                while (r.w != flag) { g.spin("att sentinel", flag, r.w); r = ld_poll4(sp); }
+            }
+        }
+    }
+    cbar();
+    for (int task = tid; task < H * 32; task += 256) {
+        const int h = task >> 5, l = task & 31;
+        const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+        const int np = c1 - c0 + 1;
+        const uint4* base = P.att_ll + (size_t)h * maxp * 33;
+        // all partials of the head in flight at once (np <= 8 in this mode), re-polled individually until complete
+        uint4 hd[8], ov[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < np) { hd[j] = ld_poll4(base + (size_t)j * 33 + 32); ov[j] = ld_poll4(base + (size_t)j * 33 + l); }
+        float M = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < np) {
+                PollGuard g;
+                while (hd[j].w != flag || ov[j].w != flag) {
+                    g.spin("att", flag, hd[j].w != flag ? hd[j].w : ov[j].w);
+                    hd[j] = ld_poll4(base + (size_t)j * 33 + 32);
+                    ov[j] = ld_poll4(base + (size_t)j * 33 + l);
+                }
+                M = fmaxf(M, __uint_as_float(hd[j].x));
+            }
+        float den = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < np) {
+                const float w = __expf(__uint_as_float(hd[j].x) - M);
+                den += w * __uint_as_float(hd[j].y);
+                n0 += w * __uint_as_float(ov[j].x); n1 += w * __uint_as_float(ov[j].y); n2 += w * __uint_as_float(ov[j].z);
+            }
+        const float inv = den > 0.f ? 1.0f / den : 0.f;
+        sx[h * D + l] = __float2bfloat16_rn(n0 * inv);
+        if (l + 32 < D) sx[h * D + l + 32] = __float2bfloat16_rn(n1 * inv);
+        if (l + 64 < D) sx[h * D + l + 64] = __float2bfloat16_rn(n2 * inv);
+    }
+    cbar();
+}
+
 // ------------------------------------------------------------------ x staging: merge of the split-KV attention partials
 __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid) {
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
@@ -302,9 +472,10 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
 }
 
 // ------------------------------------------------------------------ consumer side of one GEMV phase (x already staged)
+template <bool LL>
 __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, const __nv_bfloat16* emb_row,
                                            float* extra_out, const Smem& S, uint32_t& cnt, int tid, int warp, int lane,
-                                           long long* occ = nullptr) {
+                                           long long* occ = nullptr, unsigned out_flag = 0u) {
     const int G = gridDim.x, c = blockIdx.x;
     const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
     const int nsel = op.act == 3 ? 2 : 1;
@@ -314,11 +485,22 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     const int g = lane >> 2, t = lane & 3;
     const int nchunk2 = op.seg_len / 64;
     // residual of this thread's output column: loaded now, used in the epilogue (hides one L2 round trip)
-    const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : op.residual;
+    constexpr bool ll = LL;
+    const bool res_is_ll = ll && !(op.from_embed & 2) && op.res_ll != nullptr;
+    const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : (res_is_ll ? reinterpret_cast<const __nv_bfloat16*>(op.res_ll) : op.residual);
+    // element n of a residual vector: plain bf16, or the data half of its {2 x bf16, flag} packet (this CTA polled the whole vector
+    // when it staged the phase that consumed it, so no flag check here)
+    auto load_res = [&](int n) -> float {
+        if (res_is_ll) {
+            const uint32_t d = __ldcg(reinterpret_cast<const unsigned int*>(op.res_ll + (n >> 1)));
+            return __uint_as_float((n & 1) ? (d & 0xffff0000u) : (d << 16));
+        }
+        return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
+    };
     float res_pre = 0.f;
     if (res != nullptr && tid < nu * MEGA_ROWS) {
         const int n = (c + (tid >> 3) * G) * MEGA_ROWS + (tid & 7);
-        if (n < op.n_out) res_pre = __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
+        if (n < op.n_out) res_pre = load_res(n);
     }
     if (occ != nullptr && lane == 0) {
         // bring-up: how many of this warp's next slots have already landed when the phase starts (prefetch depth)
@@ -365,36 +547,51 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     cbar();
     // ---- epilogue: one thread per output column, segments summed in a fixed order
     unsigned long long key = 0ull;
-    for (int o = tid; o < nu * MEGA_ROWS; o += 256) {
+    const bool out_ll = ll && op.out_ll != nullptr;
+    for (int o0 = 0; o0 < nu * MEGA_ROWS; o0 += 256) {           // warp-uniform trip count: the packet store pairs lanes
+        const int o = o0 + tid;
+        const bool active = o < nu * MEGA_ROWS;
         const int j = o >> 3, col = o & 7;
         const int n = (c + j * G) * MEGA_ROWS + col;
-        if (n >= op.n_out) continue;
-        const float* pp = S.part + (size_t)j * ipu * 8 + col;
-        float a0 = 0.f;
-        for (int s = 0; s < nseg; ++s) a0 += pp[s * 8];
-        if (op.act == 3) {
-            float a1 = 0.f;
-            for (int s = 0; s < nseg; ++s) a1 += pp[(nseg + s) * 8];
-            const float gt = bf16r(a0), u = bf16r(a1);
-            reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(u * bf16r(silu_f(gt)));
-        } else {
-            float y = a0;
-            if (op.bias) y += __bfloat162float(op.bias[n]);
-            y = bf16r(y);
-            if (res) {
-                const float rv = o < 256 ? res_pre
-                                         : __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
-                y = bf16r(y + rv);
+        const bool live = active && n < op.n_out;
+        unsigned short ybits = 0;
+        if (live) {
+            const float* pp = S.part + (size_t)j * ipu * 8 + col;
+            float a0 = 0.f;
+            for (int s = 0; s < nseg; ++s) a0 += pp[s * 8];
+            if (op.act == 3) {
+                float a1 = 0.f;
+                for (int s = 0; s < nseg; ++s) a1 += pp[(nseg + s) * 8];
+                const float gt = bf16r(a0), u = bf16r(a1);
+                const __nv_bfloat16 yv = __float2bfloat16_rn(u * bf16r(silu_f(gt)));
+                ybits = __bfloat16_as_ushort(yv);
+                if (!out_ll) reinterpret_cast<__nv_bfloat16*>(op.out)[n] = yv;
+            } else {
+                float y = a0;
+                if (op.bias) y += __bfloat162float(op.bias[n]);
+                y = bf16r(y);
+                if (res) {
+                    const float rv = o < 256 ? res_pre : load_res(n);
+                    y = bf16r(y + rv);
+                }
+                ybits = __bfloat16_as_ushort(__float2bfloat16_rn(y));
+                if (!out_ll) {
+                    if (op.out_f32) reinterpret_cast<float*>(op.out)[n] = y;
+                    else reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(y);
+                }
+                if (extra_out) extra_out[n] = y;
+                if (op.argmax) {
+                    uint32_t u = __float_as_uint(y);
+                    u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+                    const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                    key = k > key ? k : key;
+                }
             }
-            if (op.out_f32) reinterpret_cast<float*>(op.out)[n] = y;
-            else reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(y);
-            if (extra_out) extra_out[n] = y;
-            if (op.argmax) {
-                uint32_t u = __float_as_uint(y);
-                u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-                const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
-                key = k > key ? k : key;
-            }
+        }
+        if (out_ll) {
+            // columns n, n + 1 (n even) of one 8-row unit sit in adjacent lanes: one 8-byte {2 x bf16, phase id} packet
+            const unsigned hi = __shfl_down_sync(0xffffffffu, (unsigned)ybits, 1);
+            if (live && !(col & 1)) st_packet2(op.out_ll + (n >> 1), (unsigned)ybits | (hi << 16), out_flag);
         }
     }
     if (op.argmax) {
@@ -584,9 +781,10 @@ __device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, 
 }
 
 // ------------------------------------------------------------------ attention phase
-template <int D>
+template <int D, bool LL>
 __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, uint32_t& cnt, int warp,
-                                                int lane) {
+                                                int lane, unsigned in_flag = 0u, unsigned out_flag = 0u) {
+    constexpr bool ll = LL;
     constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2, D4 = D + 4;
     constexpr int ROWB = D * 2, CTM = (MG_SLOT_BYTES / ROWB) & ~7, NPASS = CTM / 8;   // tokens / 8-token passes per ring item
     const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
@@ -625,12 +823,50 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
             const __nv_bfloat16* qh = qkv + (size_t)h * D;
             const __nv_bfloat16* kh = qkv + (size_t)(H + hk) * D;
             float q1[(half + 31) / 32], q2[(half + 31) / 32], k1[(half + 31) / 32], k2[(half + 31) / 32];
+            if (ll) {
+                // q / k of this head as {2 x bf16, phase id} packets written by the qkv phase: all loads first, then re-poll
+                // whatever is not there yet (the poll replaces the grid barrier AND the load that followed it)
+                constexpr int NU = (half + 31) / 32;
+                const int eq = h * D, ek = (H + hk) * D;
+                if (lane < 3) {                                     // sentinels: last packet of this head's q, k and v rows
+                    const int e = (lane == 0 ? eq : lane == 1 ? ek : (H + KVH + hk) * D) + D - 2;
+                    PollGuard g;
+                    uint2 r = ld_poll2(P.qkv_ll + (e >> 1));
+                    while (r.y != in_flag) { g.spin("qkv sentinel", in_flag, r.y); r = ld_poll2(P.qkv_ll + (e >> 1)); }
+                }
+                __syncwarp();
+                uint2 pq1[NU], pq2[NU], pk1[NU], pk2[NU];
 #pragma unroll
-            for (int u = 0; u < (half + 31) / 32; ++u) {
-                const int j = lane + u * 32;
-                if (j < half) {
-                    q1[u] = __bfloat162float(__ldcg(qh + j)); q2[u] = __bfloat162float(__ldcg(qh + j + half));
-                    k1[u] = __bfloat162float(__ldcg(kh + j)); k2[u] = __bfloat162float(__ldcg(kh + j + half));
+                for (int u = 0; u < NU; ++u) {
+                    const int j = lane + u * 32;
+                    if (j < half) {
+                        pq1[u] = ld_poll2(P.qkv_ll + ((eq + j) >> 1)); pq2[u] = ld_poll2(P.qkv_ll + ((eq + j + half) >> 1));
+                        pk1[u] = ld_poll2(P.qkv_ll + ((ek + j) >> 1)); pk2[u] = ld_poll2(P.qkv_ll + ((ek + j + half) >> 1));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int j = lane + u * 32;
+                    if (j < half) {
+                        PollGuard g;
+                        while (pq1[u].y != in_flag || pq2[u].y != in_flag || pk1[u].y != in_flag || pk2[u].y != in_flag) {
+                            g.spin("qkv", in_flag, pq1[u].y);
+                            pq1[u] = ld_poll2(P.qkv_ll + ((eq + j) >> 1)); pq2[u] = ld_poll2(P.qkv_ll + ((eq + j + half) >> 1));
+                            pk1[u] = ld_poll2(P.qkv_ll + ((ek + j) >> 1)); pk2[u] = ld_poll2(P.qkv_ll + ((ek + j + half) >> 1));
+                        }
+                        auto pick = [](uint2 pkt, int e) { return __uint_as_float((e & 1) ? (pkt.x & 0xffff0000u) : (pkt.x << 16)); };
+                        q1[u] = pick(pq1[u], eq + j); q2[u] = pick(pq2[u], eq + j + half);
+                        k1[u] = pick(pk1[u], ek + j); k2[u] = pick(pk2[u], ek + j + half);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < (half + 31) / 32; ++u) {
+                    const int j = lane + u * 32;
+                    if (j < half) {
+                        q1[u] = __bfloat162float(__ldcg(qh + j)); q2[u] = __bfloat162float(__ldcg(qh + j + half));
+                        k1[u] = __bfloat162float(__ldcg(kh + j)); k2[u] = __bfloat162float(__ldcg(kh + j + half));
+                    }
                 }
             }
 #pragma unroll
@@ -651,9 +887,21 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
         const int tend = has_new ? pos : t1;
         const __nv_bfloat16* vnew = qkv + (size_t)(H + KVH + hk) * D;
         uint4 vn[VPL];                                  // this lane's slice of the new v row
+        // 8 consecutive elements of the new v row from packets (element index e0, multiple of 8): two 16-byte loads, four flags
+        auto v8_ll = [&](int e0) -> uint4 {
+            const uint2* src = P.qkv_ll + (e0 >> 1);
+            PollGuard g;
+            uint4 a = ld_poll4(src), b = ld_poll4(src + 2);
+            while (a.y != in_flag || a.w != in_flag || b.y != in_flag || b.w != in_flag) {
+                g.spin("v", in_flag, a.y);
+                a = ld_poll4(src); b = ld_poll4(src + 2);
+            }
+            return make_uint4(a.x, a.z, b.x, b.z);
+        };
         if (has_new) {
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) vn[i] = ldcg4(vnew + sub * EPL + i * 8);
+            for (int i = 0; i < VPL; ++i)
+                vn[i] = ll ? v8_ll((H + KVH + hk) * D + sub * EPL + i * 8) : ldcg4(vnew + sub * EPL + i * 8);
             if ((h % rep) == 0 && lane < D / 8) {
                 // exactly one segment per kv head appends the new row to the cache (for FUTURE steps; this step uses the
                 // locally rotated copy, so there is no intra-phase dependency on this write)
@@ -662,7 +910,9 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                 kq.x = pack_bf16(s8[0], s8[1]); kq.y = pack_bf16(s8[2], s8[3]);
                 kq.z = pack_bf16(s8[4], s8[5]); kq.w = pack_bf16(s8[6], s8[7]);
                 *reinterpret_cast<uint4*>(kc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = kq;
-                *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = ldcg4(vnew + lane * 8);
+                *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) =
+                    ll ? v8_ll((H + KVH + hk) * D + lane * 8) : ldcg4(vnew + lane * 8);
+                __threadfence();                   // flags-in-data mode: ordered before this warp's partial packets (no barrier follows)
                 fence_proxy_async_global();        // later steps read this row with bulk copies (async proxy)
             }
         }
@@ -821,6 +1071,17 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                 }
             }
             const int c0 = (hh * ctx) / Lc;
+            if (ll) {
+                if constexpr (D <= 96) {
+                    uint4* pk = P.att_ll + ((size_t)hh * P.att_maxp + (c - c0)) * 33;
+                    float n1 = 0.f, n2 = 0.f;
+                    if constexpr (D > 32) n1 = num[1];
+                    if constexpr (D > 64) n2 = num[2];
+                    st_packet4(pk + lane, num[0], n1, n2, out_flag);       // dims lane, lane + 32, lane + 64
+                    if (lane == 0) st_packet4(pk + 32, M, L, 0.f, out_flag);
+                }
+                continue;
+            }
             float* dst = P.att_ws + ((size_t)hh * P.att_maxp + (c - c0)) * D4;
 #pragma unroll
             for (int i = 0; i < (D + 31) / 32; ++i) {
@@ -834,10 +1095,10 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
 #undef ATR
 }
 
-template <int D>
+template <int D, bool LL>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* tokens_out, float* logits_out,
-                   long long eos_id, long long pad_id) {
+                   long long eos_id, long long pad_id, unsigned flag_base) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[MG_CONSUMERS * MG_SLOTS], s_empty[MG_CONSUMERS * MG_SLOTS];
     __shared__ float s_red[MG_CONSUMERS];
@@ -906,7 +1167,8 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         return;
     }
     // ---------------------------------------------------------------- consumers
-    unsigned epoch = 0;
+    unsigned epoch = 0, bars = 0;
+    constexpr bool ll = LL;
     uint32_t cnt = 0;
     const int pos0 = P.st->ctx_len;                     // position == cache slot of the first token processed
     const int step0 = P.st->step;
@@ -926,44 +1188,64 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         MegaOp op = P.ops[0];
         NormPre np;
         prefetch_norm(op, np, tid);
+        // phase ids of this step (flags-in-data mode): flag_base + step * bps + phase + 1, phase = 5 l + {qkv, attn, o, gate_up, down}
+        const unsigned pid0 = flag_base + (unsigned)stp * (5u * P.n_layers + 2u) + 1u;
+        auto boundary = [&]() {
+            if (ll) phase_end(epoch, tid, &s_epoch);
+            else grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate);
+        };
         for (int l = 0; l < P.n_layers; ++l) {
+            const unsigned pq = pid0 + 5u * l;          // id of this layer's qkv phase
             // norm + qkv
-            if (!(ablate & 4)) stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
+            if (!(ablate & 4)) {
+                if (ll && !(op.from_embed & 1)) stage_x_ll(op, pq - 1u, S, tid, warp, lane);           // x from down(l-1)
+                else stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
+            }
             tr.mark(tid);
             long long* occ = tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ : nullptr);
+            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ : nullptr, pq);
             op = P.ops[l * 4 + 1];
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+            tr.mark(tid); boundary(); tr.mark(tid);
             // rope + KV append + split-KV attention
-            if (!(ablate & 2)) attention_phase<D>(P, l, pos, S, cnt, warp, lane);
+            if (!(ablate & 2)) attention_phase<D, LL>(P, l, pos, S, cnt, warp, lane, pq, pq + 1u);
             tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+            tr.mark(tid); boundary(); tr.mark(tid);
             // merge + o_proj + residual
-            if (!(ablate & 4)) stage_x_attn(P, S, pos + 1, tid);
+            if (!(ablate & 4)) {
+                if (ll) stage_x_attn_ll(P, pq + 1u, S, pos + 1, tid);
+                else stage_x_attn(P, S, pos + 1, tid);
+            }
             tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 8 : nullptr);
+            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 8 : nullptr, pq + 2u);
             op = P.ops[l * 4 + 2];
-            prefetch_norm(op, np, tid);
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+            if (!ll) prefetch_norm(op, np, tid);
+            tr.mark(tid); boundary(); tr.mark(tid);
             // norm + gate_up + SwiGLU
-            if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            if (!(ablate & 4)) {
+                if (ll) stage_x_ll(op, pq + 2u, S, tid, warp, lane);
+                else stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            }
             tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 16 : nullptr);
+            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 16 : nullptr, pq + 3u);
             op = P.ops[l * 4 + 3];
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+            tr.mark(tid); boundary(); tr.mark(tid);
             // down + residual
-            if (!(ablate & 4)) stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            if (!(ablate & 4)) {
+                if (ll) stage_x_ll(op, pq + 3u, S, tid, warp, lane);
+                else stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            }
             tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 24 : nullptr);
+            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 24 : nullptr, pq + 4u);
             op = P.ops[l * 4 + 4];
-            prefetch_norm(op, np, tid);
-            tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+            if (!ll) prefetch_norm(op, np, tid);
+            tr.mark(tid); boundary(); tr.mark(tid);
         }
         // norm + lm_head + bias + greedy pick
-        stage_x_vec(op, op.x, np, S, tid, warp, lane);
+        if (ll) stage_x_ll(op, pid0 + 5u * P.n_layers - 1u, S, tid, warp, lane);
+        else stage_x_vec(op, op.x, np, S, tid, warp, lane);
         tr.mark(tid);
-        gemv_items(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate); tr.mark(tid);
+        gemv_items<LL>(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
+        tr.mark(tid); grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate); tr.mark(tid);
         // ---- bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
         if (blockIdx.x == 0 && tid == 0) {
             DecodeState* st = P.st;
@@ -978,7 +1260,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             st->attn_len = pos + 1;
             st->step = step + 1;
         }
-        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, tid, &s_epoch, ablate);   // the next step reads cur_token
+        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate);   // the next step reads cur_token
     }
     if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 1] = (long long)globaltimer_ns();
 }
@@ -1070,13 +1352,34 @@ size_t decode_mega_att_ws_bytes(const MegaPlan* p) {
     return (size_t)p->heads * p->att_maxp * (p->head_dim + 4) * sizeof(float);
 }
 
+unsigned decode_mega_phase_ids(const MegaPlan* p, int n_steps) { return (unsigned)n_steps * (5u * p->n_layers + 2u); }
+
+// Flags-in-data mode needs every CTA in every phase's dependency chain (that is what bounds the skew between CTAs to one phase
+// and makes the in-place reuse of the x / qkv / mid / partial buffers safe without grid barriers): every GEMV op of a layer must
+// have at least gridDim units, outputs in whole packets; the partial packets hold 3 floats per lane -> head_dim <= 96, and the
+// merge keeps <= 8 partials per head in registers.
+bool decode_mega_ll_supported(const MegaPlan* p) {
+    const int G = num_sms();
+    if (p->head_dim > 96 || p->att_maxp > 8) return false;
+    for (int i = 0; i < p->n_layers * 4; ++i) {
+        const MegaOp& op = p->ops[i];
+        if (op.units < G || op.n_out % 8 != 0 || op.K % 4 != 0 || op.K > 8192) return false;
+    }
+    return p->ops[p->n_layers * 4].K <= 8192;
+}
+
+size_t decode_mega_att_ll_packets(const MegaPlan* p) { return (size_t)p->heads * p->att_maxp * 33; }
+
 int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
-                       long long eos_id, long long pad_id, cudaStream_t s) {
+                       long long eos_id, long long pad_id, unsigned flag_base, cudaStream_t s) {
     const size_t smem = (size_t)MG_RING_BYTES + hp->x_bytes + (size_t)hp->part_items * 32;
-    using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long);
+    using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long, unsigned);
     const int di = hp->head_dim == 64 ? 0 : hp->head_dim == 96 ? 1 : 2;
-    KernelT kern = di == 0 ? decode_mega_kernel<64> : di == 1 ? decode_mega_kernel<96> : decode_mega_kernel<128>;
-    static size_t attr_set[3] = {0, 0, 0};
+    KernelT kern = hp->use_ll ? (di == 0 ? decode_mega_kernel<64, true> : decode_mega_kernel<96, true>)
+                              : (di == 0 ? decode_mega_kernel<64, false> : di == 1 ? decode_mega_kernel<96, false>
+                                                                                 : decode_mega_kernel<128, false>);
+    static size_t attr_set_tab[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    size_t* attr_set = attr_set_tab[hp->use_ll ? 1 : 0];
     if (attr_set[di] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return GVL_ERR_CUDA;
@@ -1093,7 +1396,7 @@ int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, plan_dev, n_steps, tokens_out, logits_out, eos_id, pad_id) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, kern, plan_dev, n_steps, tokens_out, logits_out, eos_id, pad_id, flag_base) != cudaSuccess)
         return GVL_ERR_CUDA;
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;

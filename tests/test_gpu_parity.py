@@ -303,6 +303,44 @@ def test_lm_decode_single_kernel_ring_fed_kv(gvl, arch, heads, kvh, hd, ctx, mon
     lm2.close()
 
 
+def test_lm_decode_flags_in_data_full_width(gvl, monkeypatch):
+    """Phi-3.5 width (dim 3072, 32 x 96 heads, ffn 8192): the shape where the single-kernel step hands its phases over with
+    flags-in-data packets instead of grid barriers (GVL_MEGA_LL=1, opt-in). Same logits as the barrier mode and the per-op
+    chain up to accumulation-order noise, oracle parity, and repeated generate calls (phase ids keep counting across launches,
+    one-step launches of the sampling path included)."""
+    dev = "cuda"
+    P = O.make_lm_params(arch="phi3", dim=3072, heads=32, kv_heads=32, head_dim=96, ffn=8192, layers=2, vocab=1000, seed=17, std=0.02)
+    rope = O.phi35_rope_cfg(96)
+    cfg = dict(arch="phi3", layers=2, heads=32, kv_heads=32, head_dim=96, eps=1e-5, rope=rope)
+    emb = torch.randn(700, 3072, generator=torch.Generator().manual_seed(6)) * 0.05
+    outs = {}
+    for name, env in (("ll", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_LL": "1"}), ("bar", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_LL": "0"}),
+                      ("chain", {"GVL_DECODE_MEGA": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        lm = gvl.model.CausalLM(P, "phi3", 32, 32, 96, 1e-5, rope, max_ctx=1024)
+        runs = [lm.generate(inputs_embeds=emb.to(dev)[None], max_new_tokens=6, return_logits=True) for _ in range(3)]
+        samp = lm.generate(inputs_embeds=emb.to(dev)[None], max_new_tokens=6, do_sample=True, top_k=1, return_logits=True)
+        outs[name] = runs + [samp]
+        lm.close()
+    toks_ref, lg_ref = O.greedy_decode(emb.to(dev), {k: v.to(dev) for k, v in P.items()}, cfg, 6, mode="bf16")
+    tol = _logit_tol(lg_ref)
+    for name, runs in outs.items():
+        t0, l0 = runs[0]
+        for t, l in runs[1:]:
+            assert t.tolist() == t0.tolist(), name                     # deterministic across launches and step granularities
+            _cmp(l[0], l0[0], atol=1e-6)
+        same = 0
+        while same < 5 and int(t0[0, same]) == int(toks_ref[same]):
+            same += 1
+        assert same >= 2, name
+        _cmp(l0[0][: same + 1], lg_ref[: same + 1], atol=tol)
+    same = 0
+    while same < 5 and int(outs["ll"][0][0][0, same]) == int(outs["bar"][0][0][0, same]):
+        same += 1
+    _cmp(outs["ll"][0][1][0][: same + 1], outs["bar"][0][1][0][: same + 1], atol=tol)
+
+
 @pytest.mark.parametrize("mega", ["1", "0"])
 def test_sampling_decode_hf_semantics(gvl, mega, monkeypatch):
     """do_sample=True (the reference CLI default, inference.py:45-49): top_k=1 must reproduce the greedy chain step by step
