@@ -1191,7 +1191,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         // phase ids of this step (flags-in-data mode): flag_base + step * bps + phase + 1, phase = 5 l + {qkv, attn, o, gate_up, down}
         const unsigned pid0 = flag_base + (unsigned)stp * (5u * P.n_layers + 2u) + 1u;
         auto boundary = [&]() {
-            if (ll) phase_end(epoch, tid, &s_epoch);
+            if (ll && !(ablate & 16)) phase_end(epoch, tid, &s_epoch);      // ablate 16: packets AND grid barriers (isolates the data path)
             else grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate);
         };
         for (int l = 0; l < P.n_layers; ++l) {
