@@ -38,6 +38,24 @@ DECODE_BYTES_WEIGHTS = 7.447e9
 KV_BYTES_PER_CTX_TOKEN = 393216.0
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner with
+    printf at communicator creation): park the real stdout on a spare descriptor and point fd 1 at stderr for the whole run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -161,7 +179,7 @@ def run_reference_arm(args):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "detail_s": vals[-1][2]}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     return 0
 
 
@@ -372,7 +390,7 @@ def run_gvl_arm(args):
                "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms / args.steps, "api": "gvl.model.LLAVA_NEXT_VIDEO.generate(samples) with pinned host tensors"},
                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -387,6 +405,7 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gvl_arm(args)
