@@ -146,3 +146,38 @@ def warp_logits(scores, temperature=None, top_k=50, top_p=None, min_tokens_to_ke
         remove = remove_sorted.scatter(1, sorted_indices, remove_sorted)
         scores = scores.masked_fill(remove, -float("inf"))
     return scores
+
+
+# ----------------------------------------------------------------------------------------------- prompts (inference.py:90-116)
+# One-turn prompt of the reference's chat templates (datasets/chat/base_template.py:114-140) with an empty assistant slot and the
+# template's end-of-turn string removed, as create_inputs does (`chat_template.encode(conv).replace(eos, '')`).
+# (system, user prefix, assistant prefix, eos)
+_TEMPLATES = {
+    "phi3.5": ("<|system|>\nYou are a helpful AI assistant that can generate responses based on visual inputs.",
+               "\n<|user|>\n", "\n<|assistant|>\n", "<|endoftext|>"),
+    "llama3": ("<|start_header_id|>system<|end_header_id|>You are a helpful language and vision assistant. You are able to understand "
+               "the visual content that the user provides, and assist the user with a variety of tasks using natural language.",
+               "<|start_header_id|>user<|end_header_id|>", "<|start_header_id|>assistant<|end_header_id|>", "<|eot_id|>"),
+    "vicuna": ("You are a helpful language and vision assistant. You are able to understand the visual content that the user "
+               "provides, and assist the user with a variety of tasks using natural language.",
+               "\nUSER: ", "\nASSISTANT: ", "</s>"),
+}
+
+
+def build_prompt(llm, mode, text, duration=None, num_temporal_tokens=300):
+    """mode 'grounding' | 'qa' | 'referring' (inference.py:93-110). For 'referring' the "<n> seconds" mentions of `text` are
+    quantised to temporal tokens with the inference-side expression (inference.py:107)."""
+    system, user, assistant, eos = _TEMPLATES[llm]
+    if mode == "grounding":
+        question = DEFAULT_IMAGE_TOKEN + " " + GROUNDING_TOKEN + "\n" + text
+    elif mode == "qa":
+        question = DEFAULT_IMAGE_TOKEN + "\n" + text
+    elif mode == "referring":
+        question = DEFAULT_IMAGE_TOKEN + "\n" + seconds_to_token_inference(text, duration, num_temporal_tokens)
+    else:
+        raise ValueError("mode must be grounding, qa or referring")
+    if DEFAULT_IMAGE_TOKEN in question and GROUNDING_TOKEN not in question:
+        # Template._prompt re-inserts the image token in front of the stripped question (base_template.py:106-108)
+        question = (DEFAULT_IMAGE_TOKEN + "\n" + question.replace(DEFAULT_IMAGE_TOKEN, "").strip()).strip()
+    prompt = system + user + question + assistant + "" + eos
+    return prompt.replace(eos, "")

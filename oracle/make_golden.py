@@ -306,6 +306,40 @@ def gold_host_logic():
         json.dump(out, fh, indent=1)
     print("wrote host_logic.json")
 
+def golden_prompts(out_dir):
+    """inference.py:90-116 prompt construction with the reference's own chat templates (datasets/chat/base_template.py, exec'd from
+    its file with the dataclass decorators made hashable -- Python >= 3.11 rejects its mutable dataclass defaults)."""
+    import re
+    src = open(os.path.join(R.REF, "datasets", "chat", "base_template.py")).read()
+    src = src.replace("@dataclass\n", "@dataclass(unsafe_hash=True)\n")
+    src = src.replace("sys.path.append(os.path.abspath(os.path.join(__file__, \"..\", \"..\", \"..\")))", "")
+    import sys
+    import types
+    mod = types.ModuleType("ref_base_template")          # dataclasses looks the defining module up in sys.modules
+    mod.__file__ = os.path.join(R.REF, "datasets", "chat", "base_template.py")
+    sys.modules["ref_base_template"] = mod
+    ns = mod.__dict__
+    exec(compile(src, mod.__file__, "exec"), ns)
+    duration = 4257 / 29.97002997002997
+    out = []
+    for llm, T in (("phi3.5", ns["Phi_3_5_Template"]), ("llama3", ns["LLaMA3_Template"]), ("vicuna", ns["Vicuna_Template"])):
+        tpl = T()
+        for mode, text in (("grounding", "Give you a textual query: \"the man is cooking\". When does the described content occur in the video?"),
+                           ("qa", "What is the man doing?"), ("referring", "What happens between 70 seconds and 80 seconds?")):
+            if mode == "grounding":
+                q = "<image>" + " " + "<timestamp_grounding>" + "\n" + text
+            elif mode == "qa":
+                q = "<image>" + "\n" + text
+            else:
+                q = "<image>" + "\n" + re.sub(r"(\d+) seconds", lambda m: f"<{int(float(m.group(1))/duration*300)}>", text)
+            conv = [{"from": "human", "value": q}, {"from": "gpt", "value": ""}]
+            sep, eos = tpl.separator.apply()
+            out.append({"llm": llm, "mode": mode, "text": text, "duration": duration, "prompt": tpl.encode(conv).replace(eos, "")})
+    with open(os.path.join(out_dir, "prompts.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("wrote prompts.json", len(out))
+
+
 def golden_ingest(out_dir):
     """the reference's own interpolate_pos_embed_internvideo2_new (internvideo2.py:260-320) on a small synthetic
     checkpoint (orig_t_size 4 -> 8 frames, 4 x 4 spatial grid) -> tests/golden/ingest_pos_embed.npz."""
@@ -337,6 +371,7 @@ def main():
     gold_index_maps()
     gold_host_logic()
     golden_ingest(GOLD)
+    golden_prompts(GOLD)
 
 
 if __name__ == "__main__":

@@ -118,3 +118,30 @@ def test_warp_logits_matches_transformers_warpers():
         got = H.warp_logits(scores.clone(), temperature, top_k, top_p)
         assert torch.equal(torch.isinf(got), torch.isinf(ref)), (temperature, top_k, top_p)
         assert torch.equal(torch.nan_to_num(got, neginf=0.0), torch.nan_to_num(ref, neginf=0.0))
+
+
+def test_read_frames_on_the_reference_demo_video():
+    """README.md:90-94 transcript video: 4257 frames at 29.97003 fps -> duration 142.0419 s, 96 'middle' indices 21, 65, ..., 4234
+    (the same numbers the README timestamps are computed from). Runs where the reference checkout is mounted."""
+    path = "/root/reference/experiments/_3klvlS4W7A.mp4"
+    if not os.path.exists(path):
+        pytest.skip("reference demo video not present")
+    pytest.importorskip("cv2")
+    from gvl import video
+    frames, idx, fps, vlen, duration = video.read_frames(path, 8, sample="middle")
+    assert vlen == 4257 and abs(fps - 29.97003) < 1e-4 and abs(duration - 142.0419) < 1e-3
+    assert idx == H.get_frame_indices(8, 4257, sample="middle") and len(idx) == 8
+    assert frames.dtype == torch.uint8 and frames.shape[:2] == (8, 3) and frames.float().std() > 1.0
+    full = H.get_frame_indices(96, 4257, sample="middle")
+    assert full[:4] == [21, 65, 110, 154] and full[-2:] == [4189, 4234]
+    assert "%.2f" % (duration * 30 / 300) == "14.20" and "%.2f" % (duration * 239 / 300) == "113.16"
+
+
+def test_build_prompt_matches_reference_templates(gold_dir):
+    """Goldens: the reference's own Template classes exec'd from datasets/chat/base_template.py (oracle/make_golden.py)."""
+    cases = json.load(open(os.path.join(gold_dir, "prompts.json")))
+    assert len(cases) == 9
+    for e in cases:
+        assert H.build_prompt(e["llm"], e["mode"], e["text"], e["duration"]) == e["prompt"], (e["llm"], e["mode"])
+    with pytest.raises(ValueError):
+        H.build_prompt("phi3.5", "caption", "x")
