@@ -322,10 +322,23 @@ __device__ __noinline__ void stage_x_ll(const MegaOp& op, unsigned flag, const S
         }
     }
     cbar();
+    // all of this thread's packet loads are issued before the first flag is examined (one L2 round trip for the whole vector when
+    // the data is there; a per-packet poll loop would serialise up to 8 round trips); late packets are re-polled individually
+    uint4 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (tid + u * 256 < nq) raw[u] = ld_poll4(op.x_ll + (size_t)(tid + u * 256) * 2);
     uint2 xv[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-        if (tid + u * 256 < nq) xv[u] = poll_vec4(op.x_ll, tid + u * 256, flag, "x");
+        if (tid + u * 256 < nq) {
+            PollGuard g;
+            while (raw[u].y != flag || raw[u].w != flag) {
+                g.spin("x", flag, raw[u].y != flag ? raw[u].y : raw[u].w);
+                raw[u] = ld_poll4(op.x_ll + (size_t)(tid + u * 256) * 2);
+            }
+            xv[u] = make_uint2(raw[u].x, raw[u].z);
+        }
     if (op.norm_w == nullptr) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
