@@ -1,4 +1,5 @@
-"""ORACLE SUPPORT -- TEST INFRASTRUCTURE ONLY (runs only where /root/reference exists, i.e. this container).
+"""ORACLE SUPPORT -- TEST INFRASTRUCTURE ONLY (runs where /root/reference exists -- this container -- or where
+oracle/build_ref.py has installed the unmodified reference files under oracle/_ref -- the GPU box).
 
 Makes the reference (WHB139426/Grounded-Video-LLM @ e26da4e) importable under the container's newer stack
 (python 3.12, transformers 5.5, no timm/decord/av/peft) WITHOUT modifying or copying it:
@@ -17,7 +18,19 @@ import os
 import sys
 import types
 
-REF = os.environ.get("GVL_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref():
+    """/root/reference in the build container; oracle/_ref (installed by oracle/build_ref.py, travels with the gpurun
+    snapshot) on the GPU box."""
+    for cand in (os.environ.get("GVL_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "models")):
+            return cand
+    return "/root/reference"
+
+
+REF = _find_ref()
 
 
 def available():
