@@ -388,16 +388,17 @@ argmax_kernel(const float* __restrict__ logits, int n, long long* __restrict__ o
             int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (threadIdx.x == 0) out[0] = bi;
+        if (threadIdx.x == 0) out[0] = bi < n ? bi : 0;      // all-NaN logits: a valid id instead of the 0x7fffffff sentinel
     }
 }
 
 // x = embed[cur_token]; also bumps nothing. One CTA.
 __global__ void embed_token_kernel(const __nv_bfloat16* __restrict__ table, const DecodeState* __restrict__ st,
-                                   __nv_bfloat16* __restrict__ x, int dim) {
+                                   __nv_bfloat16* __restrict__ x, int dim, int vocab) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long tok = st->cur_token;
+    long long tok = st->cur_token;
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);   // ids handed in through the C ABI are not trusted
     const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tok * dim);
     for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) reinterpret_cast<uint4*>(x)[i] = src[i];
 }
@@ -478,7 +479,7 @@ step_end_kernel(const float* __restrict__ logits, int n, DecodeState* st, long l
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
         if (threadIdx.x == 0) {
-            long long tok = bi;
+            long long tok = bi < n ? bi : 0;                  // all-NaN logits: a valid id
             if (st->finished) tok = pad_id;
             else if (eos_id >= 0 && tok == eos_id) st->finished = 1;
             if (tokens_out) tokens_out[step] = tok;
@@ -556,8 +557,8 @@ int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s) {
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
 
-int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, cudaStream_t s) {
-    launch_k(embed_token_kernel, dim3(1), dim3(256), 0, s, table, st, x, dim);
+int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, int vocab, cudaStream_t s) {
+    launch_k(embed_token_kernel, dim3(1), dim3(256), 0, s, table, st, x, dim, vocab);
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }

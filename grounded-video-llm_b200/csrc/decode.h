@@ -23,7 +23,7 @@ int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv
                      float* ws, const int* ctx_len_dev, int heads, int kv_heads, int head_dim, int max_ctx,
                      float scale, cudaStream_t s);
 int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s);
-int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, cudaStream_t s);
+int embed_token(const __nv_bfloat16* table, const DecodeState* st, __nv_bfloat16* x, int dim, int vocab, cudaStream_t s);
 int rope_decode(const __nv_bfloat16* qkv, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache,
                 const __nv_bfloat16* cosb, const __nv_bfloat16* sinb, const DecodeState* st, int heads, int kv_heads,
                 int D, int max_ctx, cudaStream_t s);

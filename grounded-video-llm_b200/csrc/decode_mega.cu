@@ -1192,7 +1192,8 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         const int pos = pos0 + stp, step = step0 + stp;
         Tracer tr{tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE : nullptr};
         tr.mark(tid); tr.mark(tid); tr.mark(tid);       // (the embed phase of the first version: kept for the trace layout)
-        const long long tok = __ldcg(&P.st->cur_token);
+        long long tok = __ldcg(&P.st->cur_token);
+        tok = tok < 0 ? 0 : (tok >= P.vocab ? P.vocab - 1 : tok);      // ids set through the C ABI are not trusted
         const __nv_bfloat16* emb_row = P.embed + (size_t)tok * P.dim;
         if (tid < P.head_dim) {
             s_rope[tid] = __bfloat162float(P.rope_cos[(size_t)pos * P.head_dim + tid]);

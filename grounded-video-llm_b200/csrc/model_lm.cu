@@ -41,7 +41,8 @@ struct gvl_lm {
     long long g_eos = 0, g_pad = 0;
     bool use_graph = true;
     bool use_pdl = true;
-    // single-kernel decode step (decode_mega.cu), opt-in with GVL_DECODE_MEGA=1 until it beats the per-op kernel chain
+    int host_ctx = -1;                // tokens in the KV cache as the HOST knows them: S after prefill, += n_steps per decode call
+    // single-kernel decode step (decode_mega.cu): the default when the shape fits (GVL_DECODE_MEGA=0 selects the per-op chain)
     bool use_mega = false;
     MegaPlan* plan_dev = nullptr;
     MegaPlan* plan_host = nullptr;
@@ -101,7 +102,7 @@ int enqueue_decode_step_impl(gvl_lm* lm, long long* tokens_out, float* logits_ou
     const int qkv_n = (H + 2 * KVH) * hd;
     const float scale = 1.0f / sqrtf((float)hd);
     CK(step_begin(lm->st, s));
-    CK(embed_token((const __nv_bfloat16*)w.embed, lm->st, lm->dx, D, s));
+    CK(embed_token((const __nv_bfloat16*)w.embed, lm->st, lm->dx, D, w.vocab, s));
     for (int l = 0; l < w.n_layers; ++l) {
         const gvl_lm_layer& L = lm->layers[l];
         CK(gemv_bf16(lm->dx, D, (const __nv_bfloat16*)L.qkv_w, D, lm->dqkv, qkv_n, 1, qkv_n, D,
@@ -345,6 +346,7 @@ int gvl_lm_prefill(gvl_lm* lm, const void* embeds, int S, float* logits_out, voi
     init.ctx_len = S; init.attn_len = S; init.step = 0; init.finished = 0; init.cur_token = 0;
     CU(cudaMemcpyAsync(lm->st, &init, sizeof(init), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(&lm->st->cur_token, lm->first_tok, sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    lm->host_ctx = S;
     return GVL_OK;
 }
 
@@ -352,8 +354,9 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
                   long long pad_id, void* stream) {
     if (!lm || n_steps < 0 || n_steps > lm->w.max_ctx) return GVL_ERR_ARG;
     cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+    if (lm->host_ctx < 0) return GVL_ERR_STATE;                         // no prefill yet
+    if (lm->host_ctx + n_steps > lm->w.max_ctx) return GVL_ERR_STATE;   // step t writes K/V slot ctx + t: never past the cache
     if (n_steps == 0) return GVL_OK;
-    // The caller guarantees ctx + n_steps <= max_ctx (checked by the Python mirror, which knows S).
     // Steps run on the object's own stream (the caller's may be the legacy default stream, which cannot be
     // captured), fenced against the caller's stream with events on both sides.
     cudaStream_t s = lm->cs;
@@ -414,6 +417,7 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
     if (want_logits) CU(cudaMemcpyAsync(logits_out, lbuf, (size_t)n_steps * lm->w.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(cudaEventRecord(lm->ev_out, s));
     CU(cudaStreamWaitEvent(caller, lm->ev_out, 0));
+    lm->host_ctx += n_steps;
     return GVL_OK;
 }
 

@@ -19,6 +19,8 @@ STATUS = {
     -6: "GVL_ERR_STATE",
 }
 
+GVL_OK, GVL_ERR_ARG, GVL_ERR_ALIGN, GVL_ERR_CUDA, GVL_ERR_DRIVER, GVL_ERR_NOMEM, GVL_ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+
 _lib = None
 
 c_vp = ctypes.c_void_p

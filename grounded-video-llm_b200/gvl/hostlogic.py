@@ -98,17 +98,30 @@ def spatial_keyframes(num_frames, num_segs):
 
 
 # --------------------------------------------------------------------------------------- RoPE tables
-def longrope_tables(max_ctx, head_dim, base, short_factor, long_factor, max_pos, orig_max_pos, use_long):
-    """Phi3LongRoPEScaledRotaryEmbedding.forward (modeling_phi3.py:371-409) for positions 0..max_ctx-1 -> bf16."""
-    ext = torch.tensor(long_factor if use_long else short_factor, dtype=torch.float32)
+def longrope_tables(max_ctx, head_dim, base, short_factor, long_factor, max_pos, orig_max_pos, use_long, long_from=None):
+    """Phi3LongRoPEScaledRotaryEmbedding.forward (modeling_phi3.py:371-409) for positions 0..max_ctx-1 -> bf16.
+
+    The factor set is chosen per FORWARD CALL from `seq_len = kv_seq_len` (modeling_phi3.py:562-563, 680-686): a prefill of S
+    tokens rotates every position with long_factor iff S > original_max_position_embeddings; a cached decode step at
+    position p (kv_seq_len = p + 1) rotates ITS q / k with long_factor iff p >= original_max_position_embeddings, while the
+    keys already in the cache keep the rotation they were stored with. On the reference's inference path (generate from
+    inputs_embeds) the cache reset of prepare_inputs_for_generation (:1557-1562) never fires, because its `input_ids` holds
+    only the generated tokens. Hence one table serves a whole generate call: rows < long_from short, rows >= long_from long,
+    with long_from = 0 for a long prefill (use_long) and original_max_position_embeddings otherwise."""
+    if long_from is None:
+        long_from = 0 if use_long else max_ctx
     shape = torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim
-    inv_freq = 1.0 / (ext * base ** shape)
     pos = torch.arange(max_ctx, dtype=torch.float32)
-    freqs = pos[:, None] * inv_freq[None, :]
-    emb = torch.cat((freqs, freqs), dim=-1)
     scale = max_pos / orig_max_pos
     sf = 1.0 if scale <= 1.0 else math.sqrt(1 + math.log(scale) / math.log(orig_max_pos))
-    return (emb.cos() * sf).to(torch.bfloat16), (emb.sin() * sf).to(torch.bfloat16)
+    out = []
+    for factor in (short_factor, long_factor):
+        inv_freq = 1.0 / (torch.tensor(factor, dtype=torch.float32) * base ** shape)
+        freqs = pos[:, None] * inv_freq[None, :]
+        emb = torch.cat((freqs, freqs), dim=-1)
+        out.append(((emb.cos() * sf).to(torch.bfloat16), (emb.sin() * sf).to(torch.bfloat16)))
+    is_long = (torch.arange(max_ctx) >= long_from)[:, None]
+    return torch.where(is_long, out[1][0], out[0][0]), torch.where(is_long, out[1][1], out[0][1])
 
 
 def plain_rope_tables(max_ctx, head_dim, base, bf16_matmul_quirk=False):

@@ -130,19 +130,22 @@ class CausalLM:
         self.dim = state_dict["model.embed_tokens.weight"].shape[1]
         self._shared = None
 
-    def _tables(self, use_long):
+    def _tables(self, long_from):
         r = self.rope
         hd = self.cfg[2]
         if r["type"] == "longrope":
             return hostlogic.longrope_tables(self.max_ctx, hd, r["base"], r["short_factor"], r["long_factor"],
-                                             r["max_pos"], r["orig_max_pos"], use_long)
+                                             r["max_pos"], r["orig_max_pos"], False, long_from=long_from)
         return hostlogic.plain_rope_tables(self.max_ctx, hd, r["base"], bf16_matmul_quirk=r.get("bf16_quirk", False))
 
-    def _get(self, use_long):
-        """One C-side LM object per RoPE table (short / long factor); the weight buffers are shared."""
-        if use_long not in self._lms:
+    def _get(self, long_from):
+        """One C-side LM object per RoPE table; the weight buffers are shared. LongRoPE (modeling_phi3.py:371-409) picks the
+        factor set per forward call from kv_seq_len: `long_from` = first position rotated with long_factor -- 0 after a prompt
+        longer than original_max_position_embeddings, original_max_position_embeddings otherwise (cached decode steps past it
+        switch to long_factor while the keys already cached keep their rotation; hostlogic.longrope_tables)."""
+        if long_from not in self._lms:
             lib = _lib.load()
-            cos, sin = self._tables(use_long)
+            cos, sin = self._tables(long_from)
             h, kvh, hd, eps = self.cfg
             if self._shared is None:
                 pk = weights.pack_lm(self.sd, self.arch, h, kvh, hd, eps, self.max_ctx, cos, sin, device=self.device)
@@ -157,36 +160,33 @@ class CausalLM:
             handle = ctypes.c_void_p()
             rc = lib.gvl_lm_create(ctypes.byref(pk.struct), ctypes.byref(handle))
             _lib.check(rc, "gvl_lm_create")
-            self._lms[use_long] = handle
-        return self._lms[use_long]
+            self._lms[long_from] = handle
+        return self._lms[long_from]
 
     @property
     def embed_table(self):
-        self._get(False)
+        self._get(self._long_from(1))
         return self._shared.embed
 
     def get_input_embeddings(self):
         table = self.embed_table
         return lambda ids: table[ids]
 
-    def _use_long(self, total_len):
+    def _long_from(self, prompt_len):
         r = self.rope
         if r["type"] != "longrope":
-            return False
-        return total_len > r["orig_max_pos"]
+            return 0
+        return 0 if prompt_len > r["orig_max_pos"] else r["orig_max_pos"]
 
     def prefill(self, inputs_embeds, want_hidden=False, n_new=0):
-        """inputs_embeds [S,D] bf16. Returns (last-position fp32 logits [V], hidden [S,D] or None)."""
+        """inputs_embeds [S,D] bf16. Returns (last-position fp32 logits [V], hidden [S,D] or None). `n_new` is only a
+        capacity hint: generate() clamps the number of steps to the cache (max_new_tokens is a ceiling, not a reservation)."""
         lib = _lib.load()
         emb = inputs_embeds.to(self.device, torch.bfloat16).contiguous()
         S = emb.shape[0]
-        if S + n_new > self.max_ctx:
-            raise ValueError("sequence of %d tokens (+%d new) exceeds max_ctx=%d" % (S, n_new, self.max_ctx))
-        use_long = self._use_long(S)
-        if self._use_long(S + n_new) != use_long:
-            # modeling_phi3.py:1557-1562 recomputes the whole cache when decoding crosses original_max_position
-            raise NotImplementedError("decode crossing the LongRoPE short/long boundary is not supported")
-        lm = self._get(use_long)
+        if S > self.max_ctx:
+            raise ValueError("sequence of %d tokens exceeds max_ctx=%d" % (S, self.max_ctx))
+        lm = self._get(self._long_from(S))
         logits = torch.empty((self.vocab,), dtype=torch.float32, device=self.device)
         hidden = torch.empty((S, self.dim), dtype=torch.bfloat16, device=self.device) if want_hidden else None
         rc = lib.gvl_lm_prefill(lm, ctypes.c_void_p(emb.data_ptr()), S, ctypes.c_void_p(logits.data_ptr()),
@@ -228,12 +228,23 @@ class CausalLM:
             self._lmh = (w, b)
         return self._lmh
 
+    EOS_CHECK_EVERY = 64      # decode steps between host-side EOS checks (one 8-byte D2H read per chunk)
+
+    def _cap(self, S, max_new_tokens):
+        """max_new_tokens is a ceiling (HF stops at EOS long before the reference's default 2048, inference.py:48): token 0
+        comes from the prefill, step t consumes cache slot S+t-1 < max_ctx."""
+        n = min(int(max_new_tokens), self.max_ctx - S + 1)
+        if n < 1:
+            raise ValueError("no room to generate: prompt of %d tokens fills max_ctx=%d" % (S, self.max_ctx))
+        return n
+
     def _sample(self, inputs_embeds, attention_mask, eos_token_id, pad_token_id, max_new_tokens, temperature, top_k, top_p,
                 generator, return_logits):
         """HF sampling loop (GenerationMixin._sample, transformers==4.40.1; call site llava_next_video.py:655-661 with
         inference.py's do_sample=True, temperature=0.2): per step logits -> warpers -> softmax -> multinomial. The logits
         come from the library one step at a time; the pick happens on the device with torch (no host synchronisation), is
-        handed back with gvl_lm_set_next_token, and finished rows emit pad_token_id like HF's unfinished_sequences mask."""
+        handed back with gvl_lm_set_next_token, and finished rows emit pad_token_id like HF's unfinished_sequences mask.
+        Every EOS_CHECK_EVERY steps the `unfinished` flag is read back and the row stops early."""
         lib = _lib.load()
         B = inputs_embeds.shape[0]
         outs, logs = [], []
@@ -241,14 +252,16 @@ class CausalLM:
             emb = inputs_embeds[b]
             if attention_mask is not None:
                 emb = emb[attention_mask[b].to(emb.device).bool()]
-            logits, _ = self.prefill(emb, n_new=max_new_tokens)
-            lm, _S = self._active
-            toks = torch.empty((max_new_tokens,), dtype=torch.int64, device=self.device)
-            lg = torch.empty((max_new_tokens, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            logits, _ = self.prefill(emb)
+            lm, S = self._active
+            n_cap = self._cap(S, max_new_tokens)
+            toks = torch.full((n_cap,), int(pad_token_id), dtype=torch.int64, device=self.device)
+            lg = torch.zeros((n_cap, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
             step_logits = torch.empty((1, self.vocab), dtype=torch.float32, device=self.device)
             scratch = torch.empty((1,), dtype=torch.int64, device=self.device)
             unfinished = torch.ones((), dtype=torch.int64, device=self.device)
-            for t in range(max_new_tokens):
+            n_done = n_cap
+            for t in range(n_cap):
                 if return_logits:
                     lg[t].copy_(logits.reshape(-1))
                 scores = hostlogic.warp_logits(logits.reshape(1, -1), temperature, top_k, top_p)
@@ -257,26 +270,58 @@ class CausalLM:
                 toks[t] = nxt
                 if eos_token_id is not None:
                     unfinished = unfinished * (nxt != int(eos_token_id)).to(torch.int64)
-                if t + 1 < max_new_tokens:
+                    if (t + 1) % self.EOS_CHECK_EVERY == 0 and int(unfinished) == 0:
+                        n_done = t + 1
+                        break
+                if t + 1 < n_cap:
                     rc = lib.gvl_lm_set_next_token(lm, ctypes.c_void_p(toks[t:t + 1].data_ptr()), _stream())
                     _lib.check(rc, "gvl_lm_set_next_token")
                     rc = lib.gvl_lm_decode(lm, 1, ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(step_logits.data_ptr()),
                                            -1, int(pad_token_id), _stream())
                     _lib.check(rc, "gvl_lm_decode")
                     logits = step_logits
-            outs.append(toks)
-            logs.append(lg)
-        out = torch.stack(outs, dim=0)
-        return (out, torch.stack(logs, dim=0)) if return_logits else out
+            outs.append(toks[:n_done])
+            logs.append(lg[:n_done] if return_logits else None)
+        return self._stack_rows(outs, logs, eos_token_id, pad_token_id, return_logits)
+
+    def _stack_rows(self, outs, logs, eos_token_id, pad_token_id, return_logits):
+        """HF generate returns [B, L]: L = length at which the LAST row finished (EOS included), earlier rows padded."""
+        if eos_token_id is not None:
+            lens = []
+            for t in outs:
+                hit = (t == int(eos_token_id)).nonzero()
+                lens.append(int(hit[0]) + 1 if hit.numel() > 0 else t.shape[0])
+            L = max(lens)
+        else:
+            L = max(t.shape[0] for t in outs)
+        rows = []
+        for t in outs:
+            r = torch.full((L,), int(pad_token_id), dtype=torch.int64, device=self.device)
+            n = min(L, t.shape[0])
+            r[:n] = t[:n]
+            rows.append(r)
+        out = torch.stack(rows, dim=0)
+        if not return_logits:
+            return out
+        lrows = []
+        for lg in logs:
+            r = torch.zeros((L, self.vocab), dtype=torch.float32, device=self.device)
+            n = min(L, lg.shape[0])
+            r[:n] = lg[:n]
+            lrows.append(r)
+        return out, torch.stack(lrows, dim=0)
 
     def generate(self, inputs_embeds=None, attention_mask=None, eos_token_id=None, pad_token_id=0, do_sample=False,
                  num_beams=1, max_new_tokens=16, temperature=None, top_p=None, top_k=50, generator=None, return_logits=False,
                  **unused):
         """generate for a batch of left-padded sequences (each row is compacted with its attention_mask and run
         as an unpadded sequence: identical to the reference's varlen path because padding carries mask 0 and
-        position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, max_new_tokens].
-        do_sample=False: greedy, all steps inside the library (one launch). do_sample=True: HF sampling (temperature, top_k
-        -- HF's GenerationConfig default 50 --, top_p, multinomial), one library step per token."""
+        position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, L] like HF generate from inputs_embeds
+        (new tokens only): L = max_new_tokens when eos_token_id is None, else the step at which the last row hit EOS.
+        do_sample=False: greedy, all steps of a chunk inside the library (one launch per EOS_CHECK_EVERY steps; one launch
+        in total without EOS). do_sample=True: HF sampling (temperature, top_k -- HF's GenerationConfig default 50 --, top_p,
+        multinomial), one library step per token. Decoding across Phi-3.5's LongRoPE switch (position 4096) follows the
+        reference's cached path: see _get()."""
         if num_beams != 1:
             raise NotImplementedError("beam search is not on the reference's inference path (num_beams=1, inference.py:172)")
         if inputs_embeds.dim() == 2:
@@ -285,37 +330,39 @@ class CausalLM:
             return self._sample(inputs_embeds, attention_mask, eos_token_id, pad_token_id, max_new_tokens, temperature, top_k,
                                 top_p, generator, return_logits)
         lib = _lib.load()
-        if inputs_embeds.dim() == 2:
-            inputs_embeds = inputs_embeds[None]
         B = inputs_embeds.shape[0]
         outs, logs = [], []
+        eos = -1 if eos_token_id is None else int(eos_token_id)
         for b in range(B):
             emb = inputs_embeds[b]
             if attention_mask is not None:
                 emb = emb[attention_mask[b].to(emb.device).bool()]
-            first_logits, _ = self.prefill(emb, n_new=max_new_tokens)
+            first_logits, _ = self.prefill(emb)
             lm, S = self._active
-            toks = torch.empty((max_new_tokens,), dtype=torch.int64, device=self.device)
-            lg = torch.empty((max_new_tokens, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            n_cap = self._cap(S, max_new_tokens)
+            toks = torch.full((n_cap,), int(pad_token_id), dtype=torch.int64, device=self.device)
+            lg = torch.zeros((n_cap, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
             # token 0 is the argmax of the prefill logits; decode steps produce tokens 1..n-1
             first = ctypes.c_void_p(lib.gvl_lm_first_token(lm))
-            n_steps = max_new_tokens - 1
-            if n_steps > 0:
-                rc = lib.gvl_lm_decode(lm, n_steps, ctypes.c_void_p(toks[1:].data_ptr()),
-                                       ctypes.c_void_p(lg[1:].data_ptr() if return_logits else 0),
-                                       -1 if eos_token_id is None else int(eos_token_id), int(pad_token_id), _stream())
-                _lib.check(rc, "gvl_lm_decode")
             toks[0:1].copy_(_wrap_device_i64(first, self.device))   # first token: one device int64 owned by the lib
             if return_logits:
                 lg[0].copy_(first_logits)
-            if eos_token_id is not None:
-                toks = _apply_eos(toks, int(eos_token_id), int(pad_token_id))
-            outs.append(toks)
-            logs.append(lg)
-        out = torch.stack(outs, dim=0)
-        if return_logits:
-            return out, torch.stack(logs, dim=0)
-        return out
+            done = 1
+            chunk = (n_cap - 1) if eos < 0 else self.EOS_CHECK_EVERY
+            if eos >= 0 and int(toks[0]) == eos:
+                n_cap = 1                                             # HF: everything after EOS is pad
+            while done < n_cap:
+                n = min(chunk, n_cap - done)
+                rc = lib.gvl_lm_decode(lm, n, ctypes.c_void_p(toks[done:].data_ptr()),
+                                       ctypes.c_void_p(lg[done:].data_ptr() if return_logits else 0), eos, int(pad_token_id),
+                                       _stream())
+                _lib.check(rc, "gvl_lm_decode")
+                done += n
+                if eos >= 0 and done < n_cap and bool((toks[done - n:done] == eos).any()):
+                    break
+            outs.append(toks[:done])
+            logs.append(lg[:done] if return_logits else None)
+        return self._stack_rows(outs, logs, eos_token_id, pad_token_id, return_logits)
 
     def close(self):
         lib = _lib.load()
@@ -333,16 +380,6 @@ def _wrap_device_i64(ptr, device):
     return torch.as_tensor(h, device=device)
 
 
-def _apply_eos(toks, eos, pad):
-    """HF semantics when the FIRST token (from prefill) is already EOS: everything after is pad."""
-    t = toks.clone()
-    hit = (t == eos).nonzero()
-    if hit.numel() > 0:
-        first = int(hit[0])
-        t[first + 1:] = pad
-    return t
-
-
 class LLAVA_NEXT_VIDEO:
     """Drop-in for models/llava_next_video.py::LLAVA_NEXT_VIDEO on the inference path (phi3.5 and llama3 variants).
 
@@ -356,7 +393,12 @@ class LLAVA_NEXT_VIDEO:
     """
 
     def __init__(self, params, llm="phi3.5", tokenizer=None, num_frames=96, num_segs=12, max_txt_len=2048,
-                 lm_cfg=None, clip_cfg=None, iv2_cfg=None, max_ctx=4096, device="cuda"):
+                 lm_cfg=None, clip_cfg=None, iv2_cfg=None, max_ctx=None, max_new_tokens=2048, device="cuda"):
+        """max_ctx (KV-cache rows) defaults to what the reference CLI's defaults can reach: visual tokens + max_txt_len +
+        max_new_tokens (inference.py:44-48: 2048 / 2048), rounded up to 256 -- 7680 rows = 3.0 GB for Phi-3.5 at 96 frames."""
+        if max_ctx is None:
+            tps = (156 if llm == "phi3.5" else 64) + 16 * (num_frames // num_segs) + 1
+            max_ctx = (num_segs * tps + max_txt_len + max_new_tokens + 255) // 256 * 256
         self.llm = llm
         self.device = torch.device(device)
         self.tokenizer = tokenizer
@@ -500,6 +542,6 @@ class LLAVA_NEXT_VIDEO:
             local = merged
         toks = [local[b] for b in range(B)]
         if self.tokenizer is not None and "input_ids" not in samples:
-            text = self.tokenizer.batch_decode(torch.stack([t.cpu() for t in toks]), skip_special_tokens=True)
+            text = self.tokenizer.batch_decode([t.cpu().tolist() for t in toks], skip_special_tokens=True)
             return [t.strip() for t in text]
         return toks

@@ -63,6 +63,10 @@ def pack_clip(sd, heads, n_layers_run, device="cuda", image=336):
     scale = hd ** -0.5
     prescale = _is_pow2(scale)
     ffn = sd["vision_model.encoder.layers.0.mlp.fc1.weight"].shape[0]
+    n_pos = sd["vision_model.embeddings.position_embedding.weight"].shape[0]
+    if n_pos != (image // 14) ** 2 + 1 or tuple(pw.shape[1:]) != (3, 14, 14):
+        raise ValueError("CLIP tables do not match image=%d: %d position rows (want %d), patch kernel %s" % (
+            image, n_pos, (image // 14) ** 2 + 1, tuple(pw.shape[1:])))
     layers = (_lib.ClipLayer * n_layers_run)()
     for l in range(n_layers_run):
         p = "vision_model.encoder.layers.%d." % l
@@ -111,6 +115,13 @@ def pack_iv2(sd, heads, n_blocks_run, frames, device="cuda"):
     pw = sd["patch_embed.proj.weight"]
     D = pw.shape[0]
     ffn = sd["blocks.0.mlp.fc1.weight"].shape[0]
+    # gvl_iv2_assemble indexes pos_embed by token: a checkpoint that was not temporally interpolated to `frames` (4-frame
+    # checkpoint = 1025 rows, internvideo2.py:260-320) would be read out of bounds instead of failing
+    if sd["pos_embed"].shape[-2] != 1 + frames * 256 or sd["pos_embed"].shape[-1] != D:
+        raise ValueError("InternVideo2 pos_embed has %d rows, want 1 + %d*256 (interpolate it first: gvl.ingest)" % (
+            sd["pos_embed"].shape[-2], frames))
+    if sd["blocks.0.attn.q_norm.weight"].numel() != D or sd["blocks.0.attn.k_norm.weight"].numel() != D or D % heads:
+        raise ValueError("InternVideo2 q_norm / k_norm must span the flattened %d-wide q / k rows" % D)
     blocks = (_lib.Iv2Block * n_blocks_run)()
     hd = D // heads
     hdp = (hd + 31) // 32 * 32          # 88 -> 96: TMA / tcgen05 friendly head stride; pad rows are exact zeros

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""inference.py of the reference (WHB139426/Grounded-Video-LLM, inference.py:14-215) on the gvl-b200 path: same flags, same three
+"""inference.py of the reference (WHB139426/Grounded-Video-LLM, inference.py:14-215) on the gvl-b200 path: same flags (--dtype accepts bfloat16 only; --model / --stage /
+--lora / --attn_implementation are accepted and have one implementation here), same three
 examples (temporal grounding, referring, video QA), same prompt construction and timestamp decoding.
 
     video file --(gvl.video.read_frames: 96 'middle' frames)--> uint8 frames on the GPU
@@ -22,11 +23,25 @@ for p in (ROOT, os.path.join(ROOT, "grounded-video-llm_b200")):
         sys.path.insert(0, p)
 
 
-def parse_args():
+def _dtype_flag(s):
+    name = str(s).replace("torch.", "").lower()
+    if name not in ("bfloat16", "bf16"):
+        raise argparse.ArgumentTypeError("the gvl-b200 path computes in bfloat16 only (reference default, inference.py:18); got %r" % s)
+    return "bfloat16"
+
+
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--llm", default="phi3.5", choices=["llama3", "phi3.5"])
+    # flags of the reference CLI that select things this path fixes (inference.py:18-29): accepted and validated, so a reference
+    # command line keeps working; bf16 is the only arithmetic the kernels implement, attention is always the fused kernel
+    ap.add_argument("--dtype", default="torch.bfloat16", type=_dtype_flag)
+    ap.add_argument("--model", default="llava_next_video", choices=["llava_next_video"])
+    ap.add_argument("--stage", default="sft", choices=["pretrain", "grounded", "sft"])
+    ap.add_argument("--lora", type=lambda s: str(s).lower() not in ("0", "false", "no", ""), default=True)
+    ap.add_argument("--attn_implementation", default="flash_attention_2", choices=["eager", "flash_attention_2"])
+    ap.add_argument("--llm", default="phi3.5", choices=["llama3", "vicuna", "phi3.5"])
     ap.add_argument("--max_txt_len", type=int, default=2048)
     ap.add_argument("--num_temporal_tokens", type=int, default=300)
     ap.add_argument("--num_frames", type=int, default=96)
@@ -48,7 +63,10 @@ def parse_args():
     ap.add_argument("--temperature", type=float, default=0.2)
     ap.add_argument("--top_p", type=float, default=None)
     ap.add_argument("--synthetic", action="store_true", help="random-init reduced-depth model + stand-in tokenizer (no weights needed)")
-    return ap.parse_args()
+    args = ap.parse_args(argv)
+    if args.llm == "vicuna":
+        ap.error("--llm vicuna: only the phi3.5 and llama3 checkpoints of the reference README are on the gvl-b200 path")
+    return args
 
 
 class ByteTokenizer:
@@ -67,7 +85,7 @@ class ByteTokenizer:
 
     def batch_decode(self, ids, skip_special_tokens=True):
         out = []
-        for row in ids.tolist():
+        for row in (ids.tolist() if hasattr(ids, "tolist") else ids):
             s = []
             for t in row:
                 if 3 <= t < self.base:
@@ -88,8 +106,8 @@ def build_model(args):
             lm=dict(synth.PHI35, layers=2, vocab=len(tok), dim=512, heads=8, kv_heads=8, head_dim=64, ffn=1024),
             clip=dict(synth.CLIP_L336, layers=3), iv2=dict(synth.IV2_1B, depth=3, gamma=0.1), lm_dtype=torch.float32)
         return model.LLAVA_NEXT_VIDEO(params, llm="phi3.5", tokenizer=tok, num_frames=args.num_frames, num_segs=args.num_segs,
-                                      max_txt_len=args.max_txt_len, lm_cfg=lm_cfg, clip_cfg=clip_cfg, iv2_cfg=iv2_cfg, max_ctx=8192,
-                                      device=args.device), tok
+                                      max_txt_len=args.max_txt_len, lm_cfg=lm_cfg, clip_cfg=clip_cfg, iv2_cfg=iv2_cfg,
+                                      max_new_tokens=args.max_new_tokens, device=args.device), tok
     from transformers import AutoTokenizer
     tok = AutoTokenizer.from_pretrained(args.tokenizer_path, use_fast=args.llm == "phi3.5")
     if args.llm == "phi3.5":
@@ -97,7 +115,10 @@ def build_model(args):
     else:
         tok.eos_token_id, tok.pad_token_id = 128009, 128001                 # llava_next_video.py:102-103
     tok.add_tokens(["<%d>" % i for i in range(args.num_temporal_tokens + 1)] + ["<timestamp_grounding>"])   # :234-236
-    cfg = json.load(open(os.path.join(args.config_path, "config.json")))
+    # the LM is built from <pretrained_vision_proj_llm_path>/language_model_seperated/config.json (llava_next_video.py:146-148);
+    # config_path only supplies the vision config
+    lm_cfg_path = os.path.join(args.pretrained_vision_proj_llm_path, "language_model_seperated", "config.json")
+    cfg = json.load(open(lm_cfg_path if os.path.exists(lm_cfg_path) else os.path.join(args.config_path, "config.json")))
     if args.llm == "phi3.5":
         rs = cfg["rope_scaling"]
         lm_cfg = dict(arch="phi3", heads=cfg["num_attention_heads"], kv_heads=cfg["num_key_value_heads"],
@@ -112,7 +133,8 @@ def build_model(args):
     params = ingest.load_params(args.llm, args.pretrained_vision_proj_llm_path, args.pretrained_video_path, args.ckpt_path,
                                 args.num_frames, args.num_segs)
     return model.LLAVA_NEXT_VIDEO(params, llm=args.llm, tokenizer=tok, num_frames=args.num_frames, num_segs=args.num_segs,
-                                  max_txt_len=args.max_txt_len, lm_cfg=lm_cfg, device=args.device), tok
+                                  max_txt_len=args.max_txt_len, lm_cfg=lm_cfg, max_new_tokens=args.max_new_tokens,
+                                  device=args.device), tok
 
 
 def create_inputs(args, mode, pixels, duration):
@@ -124,13 +146,32 @@ def create_inputs(args, mode, pixels, duration):
             "temporal_pixel_values": pixels["temporal_pixel_values"], "spatial_pixel_values": pixels["spatial_pixel_values"]}
 
 
-def main():
-    args = parse_args()
+def _synthetic_clip(path, n=300, fps=25.0, size=(480, 360)):
+    """--synthetic without a video file: write a small moving-pattern mp4 so that decode + frame sampling still run."""
+    import cv2
+    import numpy as np
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), fps, size)
+    if not w.isOpened():
+        raise RuntimeError("cannot create the synthetic clip %s" % path)
+    for i in range(n):
+        f = np.zeros((size[1], size[0], 3), np.uint8)
+        f[:, :, 0] = (i * 255) // n
+        cv2.circle(f, (40 + (i * (size[0] - 80)) // n, size[1] // 2), 30, (0, 255, 255), -1)
+        w.write(f)
+    w.release()
+    return path
+
+
+def main(argv=None):
+    args = parse_args(argv)
     import torch
     from gvl import hostlogic, preprocess, video
     torch.manual_seed(args.seed)
     if not torch.cuda.is_available():
         raise RuntimeError("inference_gvl.py needs a CUDA device: the gvl hot path has no CPU fallback")
+    if args.synthetic and not os.path.exists(args.video_path):
+        import tempfile
+        args.video_path = _synthetic_clip(os.path.join(tempfile.gettempdir(), "gvl_synthetic_clip.mp4"))
     model, _tok = build_model(args)
     frames, _idx, _fps, _vlen, duration = video.read_frames(args.video_path, args.num_frames, sample="middle")
     pixels = preprocess.create_pixel_inputs(frames.to(args.device), args.num_frames, args.num_segs)
@@ -149,6 +190,7 @@ def main():
     print("\n******videoqa example******")
     print(results["qa"][0])
     print(results["qa"][1])
+    return results
 
 
 if __name__ == "__main__":

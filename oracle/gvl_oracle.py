@@ -285,21 +285,34 @@ def splice_embeds(ids, embed_table, visual, vis_last=False):
 
 
 # ----------------------------------------------------------------------------- LLM
-def phi3_rope_tables(positions, head_dim, base, short_factor, long_factor, max_pos, orig_max_pos, seq_len=None):
+def phi3_rope_tables(positions, head_dim, base, short_factor, long_factor, max_pos, orig_max_pos, seq_len=None,
+                     long_from=None):
     """Phi3LongRoPEScaledRotaryEmbedding.forward (modeling_phi3.py:371-409). Returns fp32 cos, sin [S, head_dim]
-    BEFORE the cast to the activation dtype (the caller rounds to bf16 in bf16 mode)."""
+    BEFORE the cast to the activation dtype (the caller rounds to bf16 in bf16 mode).
+    One forward call uses ONE factor set, picked from seq_len (= kv_seq_len at the call sites, :562-563, 680-686).
+    `long_from` restates the KV-CACHED generate path in a no-cache forward: position p carries the rotation of the call that
+    produced it -- long_factor iff p >= long_from (a cached decode step at position p has kv_seq_len = p + 1; the keys already
+    in the cache are not re-rotated, and prepare_inputs_for_generation's reset (:1557-1562) never fires when generating from
+    inputs_embeds because its input_ids holds only the generated tokens)."""
     positions = positions.to(torch.float32)
-    if seq_len is None:
-        seq_len = int(positions.max().item()) + 1
-    ext = torch.tensor(long_factor if seq_len > orig_max_pos else short_factor, dtype=torch.float32,
-                       device=positions.device)
     shape = torch.arange(0, head_dim, 2, dtype=torch.int64, device=positions.device).float() / head_dim
-    inv_freq = 1.0 / (ext * base ** shape)
-    freqs = positions[:, None] * inv_freq[None, :]
-    emb = torch.cat([freqs, freqs], dim=-1)
     scale = max_pos / orig_max_pos
     sf = 1.0 if scale <= 1.0 else math.sqrt(1 + math.log(scale) / math.log(orig_max_pos))
-    return emb.cos() * sf, emb.sin() * sf
+
+    def table(factor):
+        ext = torch.tensor(factor, dtype=torch.float32, device=positions.device)
+        inv_freq = 1.0 / (ext * base ** shape)
+        freqs = positions[:, None] * inv_freq[None, :]
+        emb = torch.cat([freqs, freqs], dim=-1)
+        return emb.cos() * sf, emb.sin() * sf
+
+    if long_from is not None:
+        (cs, ss), (cl, sl) = table(short_factor), table(long_factor)
+        is_long = (positions >= long_from)[:, None]
+        return torch.where(is_long, cl, cs), torch.where(is_long, sl, ss)
+    if seq_len is None:
+        seq_len = int(positions.max().item()) + 1
+    return table(long_factor if seq_len > orig_max_pos else short_factor)
 
 
 def plain_rope_tables(positions, head_dim, base, bf16_matmul_quirk=False):
@@ -341,7 +354,7 @@ def lm_forward(embeds, P, cfg, mode="bf16", positions=None, return_hidden=False)
     rp = cfg["rope"]
     if rp["type"] == "longrope":
         cos, sin = phi3_rope_tables(positions, hd, rp["base"], rp["short_factor"], rp["long_factor"], rp["max_pos"],
-                                    rp["orig_max_pos"], seq_len=rp.get("seq_len"))
+                                    rp["orig_max_pos"], seq_len=rp.get("seq_len"), long_from=rp.get("long_from"))
     else:
         cos, sin = plain_rope_tables(positions, hd, rp["base"], bf16_matmul_quirk=(mode == "bf16" and rp.get("bf16_quirk", False)))
     cos, sin = _r(cos, mode), _r(sin, mode)
@@ -393,9 +406,15 @@ def greedy_decode(embeds, P, cfg, n_new, mode="bf16", eos_id=None, pad_id=0):
     """Teacher-forced restatement of HF GenerationMixin greedy search driven by inputs_embeds
     (transformers==4.40.1, called at llava_next_video.py:655-661): step 0 consumes inputs_embeds, every later
     step consumes the embedding of the previous argmax; finished rows emit pad_id. Recomputes the full
-    no-cache forward each step (mathematically identical to the KV-cached path)."""
+    no-cache forward each step (mathematically identical to the KV-cached path) -- with LongRoPE that needs
+    the per-position factor choice of the cached path (phi3_rope_tables `long_from`): a prompt of S <= original_max rotates
+    positions < original_max with short_factor and later ones with long_factor; a longer prompt uses long_factor throughout."""
     table = P["model.embed_tokens.weight"].float()
     seq = _r(embeds.float(), mode)
+    if cfg["rope"]["type"] == "longrope" and "long_from" not in cfg["rope"]:
+        rp = dict(cfg["rope"])
+        rp["long_from"] = rp["orig_max_pos"] if seq.shape[0] <= rp["orig_max_pos"] else 0
+        cfg = dict(cfg, rope=rp)
     toks, all_logits = [], []
     finished = False
     for _ in range(n_new):

@@ -123,6 +123,26 @@ def build_lm(arch, cfg, state_dict=None, device="cpu", dtype=torch.bfloat16):
     return m.to(dtype)
 
 
+def use_flash_attention(m):
+    """Switch a constructed Phi3ForCausalLM / LlamaForCausalLM to the reference's own FlashAttention2 classes
+    (modeling_phi3.py:613-920, modeling_llama.py:402-594) -- what `attn_implementation="flash_attention_2"` selects in the
+    reference (llava_next_video.py:146-148). Done after construction because transformers 5.x refuses the string at
+    __init__ for model classes that only carry the old `_supports_flash_attn_2` attribute. The FlashAttention2 classes
+    subclass the eager ones and add no parameters, so re-classing the modules is exact."""
+    mods = R.import_models()
+    for sub in m.modules():
+        if type(sub) is mods["phi3"].Phi3Attention:
+            sub.__class__ = mods["phi3"].Phi3FlashAttention2
+            sub._flash_attn_uses_top_left_mask = False           # flash_attn >= 2.1 (modeling_phi3.py:625-627)
+        elif type(sub) is mods["llama"].LlamaAttention:
+            sub.__class__ = mods["llama"].LlamaFlashAttention2
+            sub._flash_attn_uses_top_left_mask = False
+        if isinstance(getattr(sub, "_attn_implementation", None), str) and not hasattr(type(sub), "_attn_implementation"):
+            sub._attn_implementation = "flash_attention_2"       # Phi3Model keeps its own copy (modeling_phi3.py:1235)
+    m.config._attn_implementation_internal = "flash_attention_2"  # LlamaModel reads the config (modeling_llama.py:1047)
+    return m
+
+
 class RefVLM:
     """Stand-in for a constructed LLAVA_NEXT_VIDEO: holds the reference's sub-modules and exposes the reference's own
     encode_images / prepare_multimodal_inputs / reshape_hd_patches_2x2merge_phi3 / add_image_newline_phi3, extracted
@@ -215,13 +235,11 @@ def build_vlm(params, llm="phi3.5", lm_cfg=None, frames_per_seg=8, clip_kw=None,
     D = params["video_projecter"]["down_proj.weight"].shape[0]
     if with_lm:
         arch = "phi3" if llm == "phi3.5" else "llama"
-        attn = "flash_attention_2" if flash else "eager"
         kw = dict(lm_kw or {})
-        if arch == "phi3":
-            cfg = phi3_config(rope=lm_cfg["rope"], attn=attn, **kw)
-        else:
-            cfg = llama_config(attn=attn, **kw)
+        cfg = phi3_config(rope=lm_cfg["rope"], **kw) if arch == "phi3" else llama_config(**kw)
         lm = build_lm(arch, cfg, params["language_model"], device=device)
+        if flash:
+            use_flash_attention(lm)
     with torch.device(device):
         vp = src_cls["Video_Projecter"](params["video_projecter"]["up_proj.weight"].shape[1], D).eval()
         vp.load_state_dict(params["video_projecter"])

@@ -479,3 +479,77 @@ def test_pipeline_small_llama_variant(gvl):
     _cmp(logits, ref_logits, atol=_logit_tol(ref_logits))
     toks = m.generate(samples, max_new_tokens=3)[0]
     assert toks.shape == (3,)
+
+
+@pytest.mark.parametrize("mega", ["1", "0"])
+def test_lm_decode_across_longrope_switch(gvl, mega, monkeypatch):
+    """L10: greedy decode that crosses original_max_position_embeddings inside one generate call. The reference's cached path
+    keeps the keys stored before the switch (short_factor rotation) and rotates positions >= original_max with long_factor
+    (modeling_phi3.py:562-563, 680-686; no cache reset when generating from inputs_embeds, :1557-1562 -- pinned on CPU against
+    the reference's own cached decode by tests/test_oracle_golden.py::test_phi3_cached_decode_across_longrope_switch).
+    Here: original_max = 24, prompt S = 20, 12 new tokens (positions 20..31), teacher-forced oracle logits."""
+    monkeypatch.setenv("GVL_DECODE_MEGA", mega)
+    P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=2, vocab=1000, seed=21, std=0.05)
+    rope = dict(O.phi35_rope_cfg(64), orig_max_pos=24, max_pos=768)
+    cfg = dict(arch="phi3", layers=2, heads=4, kv_heads=4, head_dim=64, eps=1e-5, rope=rope)
+    emb = torch.randn(20, 256, generator=torch.Generator().manual_seed(22)) * 0.5
+    lm = gvl.model.CausalLM(P, "phi3", 4, 4, 64, 1e-5, rope, max_ctx=64)
+    toks, lg = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=12, return_logits=True)
+    toks_ref, lg_ref = O.greedy_decode(emb, P, cfg, 12, mode="bf16")
+    # teacher-force the oracle with gvl's tokens so that one near-tie does not derail the rest of the comparison
+    table = O.bf(P["model.embed_tokens.weight"].float())
+    seq = torch.cat([O.bf(emb), table[toks[0, :-1].cpu()]], 0)
+    rp = dict(rope, long_from=24)
+    tf = O.lm_forward(seq, P, dict(cfg, rope=rp), mode="bf16")[19:]
+    _cmp(lg[0], tf, atol=_logit_tol(tf))
+    # the switch is visible: the same sequence with ONE factor set throughout (short, or long = a cache reset) is further away
+    for other in (dict(rope, long_from=10 ** 6), dict(rope, long_from=0)):
+        alt = O.lm_forward(seq, P, dict(cfg, rope=other), mode="bf16")[19:]
+        assert float((alt[6:] - tf[6:]).abs().max()) > 4 * float((lg[0].cpu()[6:] - tf[6:]).abs().max())
+    # a prompt longer than original_max uses long_factor for every position (prefill + decode)
+    emb2 = torch.randn(30, 256, generator=torch.Generator().manual_seed(23)) * 0.5
+    toks2, lg2 = lm.generate(inputs_embeds=emb2.cuda()[None], max_new_tokens=4, return_logits=True)
+    seq2 = torch.cat([O.bf(emb2), table[toks2[0, :-1].cpu()]], 0)
+    tf2 = O.lm_forward(seq2, P, dict(cfg, rope=dict(rope, long_from=0)), mode="bf16")[29:]
+    _cmp(lg2[0], tf2, atol=_logit_tol(tf2))
+    lm.close()
+
+
+def test_generate_cap_chunks_and_abi_bounds(gvl):
+    """max_new_tokens is a ceiling: generation stops at EOS (checked between chunks of EOS_CHECK_EVERY steps), is clamped to
+    the KV cache, and the C ABI itself refuses a decode that would write past max_ctx or that precedes a prefill."""
+    import ctypes
+    from gvl import _lib
+    P = O.make_lm_params(arch="phi3", dim=256, heads=4, kv_heads=4, head_dim=64, ffn=512, layers=2, vocab=1000, seed=9, std=0.05)
+    rope = O.phi35_rope_cfg(64)
+    lm = gvl.model.CausalLM(P, "phi3", 4, 4, 64, 1e-5, rope, max_ctx=256)
+    lm.EOS_CHECK_EVERY = 4
+    emb = torch.randn(10, 256, generator=torch.Generator().manual_seed(1)) * 0.5
+    free = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=40)[0].tolist()
+    assert len(free) == 40
+    eos = free[9]
+    first = free.index(eos)
+    got = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=2048, eos_token_id=eos, pad_token_id=7)[0].tolist()
+    assert got == free[:first + 1]                                   # stops right after EOS although the ceiling is 2048
+    # clamp to the cache: prompt 10 + at most 247 tokens (token 0 needs no slot)
+    full = lm.generate(inputs_embeds=emb.cuda()[None], max_new_tokens=2048)[0]
+    assert full.shape[0] == 256 - 10 + 1 and full[:40].tolist() == free
+    # C ABI bounds
+    lib = _lib.load()
+    h = lm._active[0]
+    scratch = torch.empty((8,), dtype=torch.int64, device="cuda")
+    rc = lib.gvl_lm_decode(h, 1, ctypes.c_void_p(scratch.data_ptr()), None, -1, 0, None)
+    assert rc == _lib.GVL_ERR_STATE                                  # the cache is full after the clamped run
+    lm2 = gvl.model.CausalLM(P, "phi3", 4, 4, 64, 1e-5, dict(rope, orig_max_pos=8192), max_ctx=64)
+    h2 = lm2._get(lm2._long_from(1))
+    rc = lib.gvl_lm_decode(h2, 1, ctypes.c_void_p(scratch.data_ptr()), None, -1, 0, None)
+    assert rc == _lib.GVL_ERR_STATE                                  # no prefill yet
+    # an out-of-range id handed in through gvl_lm_set_next_token is clamped, not dereferenced
+    lm2.prefill(emb.cuda())
+    bad = torch.tensor([10 ** 12], dtype=torch.int64, device="cuda")
+    assert lib.gvl_lm_set_next_token(h2, ctypes.c_void_p(bad.data_ptr()), None) == 0
+    assert lib.gvl_lm_decode(h2, 1, ctypes.c_void_p(scratch.data_ptr()), None, -1, 0, None) == 0
+    torch.cuda.synchronize()
+    assert 0 <= int(scratch[0]) < 1000
+    lm.close()
+    lm2.close()
