@@ -255,11 +255,10 @@ int launch_attn(const AttnArgs& a, cudaStream_t stream) {
     constexpr int LDS = HD + 8;
     constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * LDS * 2;
     auto kern = attn_fwd_kernel<HD, CAUSAL>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0ull;
+    if (first_use_on_device(attr_devs)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
             return GVL_ERR_CUDA;
-        attr_set = true;
     }
     dim3 grid((a.sq + ATT_BM - 1) / ATT_BM, a.heads, a.batch);
     kern<<<grid, ATT_THREADS, SMEM, stream>>>(a);

@@ -412,10 +412,9 @@ int launch_tc3(const AttnArgs& a, cudaStream_t stream) {
     if ((rc = make_tmap_4d_attn(&tk, a.k, HD, a.skv, a.kv_heads, a.batch, a.k_ts, a.k_hs, a.k_bs)) != GVL_OK) return rc;
     if ((rc = make_tmap_4d_attn(&tv, a.v, HD, a.skv, a.kv_heads, a.batch, a.v_ts, a.v_hs, a.v_bs)) != GVL_OK) return rc;
     auto kern = attn_tc3_kernel<HD, CAUSAL, ROUND>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0ull;
+    if (first_use_on_device(attr_devs)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GVL_ERR_CUDA;
-        attr_set = true;
     }
     Atc3Params p;
     p.o = a.o; p.o_bs = a.o_bs; p.o_ts = a.o_ts; p.o_hs = a.o_hs;

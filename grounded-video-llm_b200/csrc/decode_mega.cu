@@ -1392,8 +1392,10 @@ int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps
     KernelT kern = hp->use_ll ? (di == 0 ? decode_mega_kernel<64, true> : decode_mega_kernel<96, true>)
                               : (di == 0 ? decode_mega_kernel<64, false> : di == 1 ? decode_mega_kernel<96, false>
                                                                                  : decode_mega_kernel<128, false>);
-    static size_t attr_set_tab[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    size_t* attr_set = attr_set_tab[hp->use_ll ? 1 : 0];
+    static size_t attr_set_tab[64][2][3] = {};         // per device (cudaFuncSetAttribute is per device), per kernel variant
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t* attr_set = attr_set_tab[dev & 63][hp->use_ll ? 1 : 0];
     if (attr_set[di] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return GVL_ERR_CUDA;

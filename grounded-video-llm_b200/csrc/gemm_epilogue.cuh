@@ -21,11 +21,41 @@ struct GemmParams2 {
 enum { EPI_ACT_NONE = 0, EPI_ACT_GELU = 1, EPI_ACT_QUICKGELU = 2, EPI_ACT_SWIGLU = 3 };
 enum { EPI_RES_NONE = 0, EPI_RES_BF16 = 1, EPI_RES_F32 = 2 };
 
+// The 32 bias values of a chunk (4 x 16 bytes; zeros where there is no bias / past N). Split from the math so that a caller can
+// issue these loads a chunk ahead: with 2 epilogue warps per scheduler nothing else hides their latency (the IV2 fc1 capture had
+// the epilogue warps on stall_long_sb at the first bias use, profiles/r2_gemm.md).
+__device__ __forceinline__ void epilogue_load_bias(const GemmParams2& p, int col_in, uint4 (&b4)[4]) {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) b4[g8] = make_uint4(0u, 0u, 0u, 0u);
+    if (p.bias != nullptr && col_in < p.N) {
+        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col_in);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8)
+            if (col_in + g8 * 8 < p.N) b4[g8] = __ldg(bp + g8);
+    }
+}
+
+// The 32 bf16 residual values of a chunk (RES_BF16), loadable a chunk ahead for the same reason. The residual may alias the
+// output (in-place residual stream): a chunk is read before ITS columns are written, other chunks touch other columns.
+__device__ __forceinline__ void epilogue_load_res_bf16(const GemmParams2& p, int row, bool row_ok, int col_out, int n_out_total,
+                                                       uint4 (&r4)[4]) {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) r4[g8] = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok && col_out < n_out_total) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + size_t(row) * p.ldr + col_out);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8)
+            if (col_out + g8 * 8 < n_out_total) r4[g8] = rp[g8];
+    }
+}
+
 // acc: 32 fp32 accumulator columns starting at GEMM column col_in (SWIGLU: the gate columns; accu = the matching up
-// columns). Writes 32 output columns starting at col_out of row `row`.
+// columns). Writes 32 output columns starting at col_out of row `row`. b4: epilogue_load_bias(p, col_in);
+// r4: epilogue_load_res_bf16(...) when RES == EPI_RES_BF16 (ignored otherwise).
 template <int ACT, int RES, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk32(const GemmParams2& p, const uint32_t (&acc)[32], const uint32_t (&accu)[32],
-                                                 int row, bool row_ok, int col_in, int col_out, int n_out_total) {
+                                                 int row, bool row_ok, int col_in, int col_out, int n_out_total,
+                                                 const uint4 (&b4)[4], const uint4 (&r4)[4]) {
     float v[32];
     if (ACT == EPI_ACT_SWIGLU) {
 #pragma unroll
@@ -38,26 +68,30 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams2& p, const uin
     } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        if (p.bias != nullptr && col_in < p.N) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col_in);
+        if (p.bias != nullptr) {                       // x + 0.0f is exact, so the zero-filled groups need no guard
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-                if (col_in + g8 * 8 < p.N) {
-                    const uint4 b = __ldg(bp + g8);
-                    float2 f;
-                    f = unpack_bf16(b.x); v[g8 * 8 + 0] += f.x; v[g8 * 8 + 1] += f.y;
-                    f = unpack_bf16(b.y); v[g8 * 8 + 2] += f.x; v[g8 * 8 + 3] += f.y;
-                    f = unpack_bf16(b.z); v[g8 * 8 + 4] += f.x; v[g8 * 8 + 5] += f.y;
-                    f = unpack_bf16(b.w); v[g8 * 8 + 6] += f.x; v[g8 * 8 + 7] += f.y;
-                }
+                const uint4 b = b4[g8];
+                float2 f;
+                f = unpack_bf16(b.x); v[g8 * 8 + 0] += f.x; v[g8 * 8 + 1] += f.y;
+                f = unpack_bf16(b.y); v[g8 * 8 + 2] += f.x; v[g8 * 8 + 3] += f.y;
+                f = unpack_bf16(b.z); v[g8 * 8 + 4] += f.x; v[g8 * 8 + 5] += f.y;
+                f = unpack_bf16(b.w); v[g8 * 8 + 6] += f.x; v[g8 * 8 + 7] += f.y;
             }
         }
+        // the activation result is a bf16 tensor in the reference; when nothing but the final pack follows (no LayerScale, no
+        // residual) that pack IS the rounding, so the explicit round-trip is skipped (bf16r is idempotent)
+        const bool round_act = (p.gamma != nullptr) || RES != EPI_RES_NONE || OUT_F32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float x = bf16r(v[j]);  // what nn.Linear returns under bf16 autocast
-            if (ACT == EPI_ACT_GELU) x = bf16r(gelu_erf(x));
+            if (ACT == EPI_ACT_GELU) x = gelu_erf(x);
             if (ACT == EPI_ACT_QUICKGELU) x = quick_gelu_bf16(x);
             v[j] = x;
+        }
+        if (ACT == EPI_ACT_GELU && round_act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = bf16r(v[j]);
         }
     }
     if (!row_ok || col_out >= n_out_total) return;
@@ -75,18 +109,14 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams2& p, const uin
         }
     }
     if (RES == EPI_RES_BF16) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                         size_t(row) * p.ldr + col_out);
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-            if (col_out + g8 * 8 < n_out_total) {
-                const uint4 r = rp[g8];
-                float2 f;
-                f = unpack_bf16(r.x); v[g8 * 8 + 0] += f.x; v[g8 * 8 + 1] += f.y;
-                f = unpack_bf16(r.y); v[g8 * 8 + 2] += f.x; v[g8 * 8 + 3] += f.y;
-                f = unpack_bf16(r.z); v[g8 * 8 + 4] += f.x; v[g8 * 8 + 5] += f.y;
-                f = unpack_bf16(r.w); v[g8 * 8 + 6] += f.x; v[g8 * 8 + 7] += f.y;
-            }
+            const uint4 r = r4[g8];                    // zero-filled past the edge (those columns are not stored)
+            float2 f;
+            f = unpack_bf16(r.x); v[g8 * 8 + 0] += f.x; v[g8 * 8 + 1] += f.y;
+            f = unpack_bf16(r.y); v[g8 * 8 + 2] += f.x; v[g8 * 8 + 3] += f.y;
+            f = unpack_bf16(r.z); v[g8 * 8 + 4] += f.x; v[g8 * 8 + 5] += f.y;
+            f = unpack_bf16(r.w); v[g8 * 8 + 6] += f.x; v[g8 * 8 + 7] += f.y;
         }
     } else if (RES == EPI_RES_F32) {
         const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) +
@@ -119,6 +149,16 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams2& p, const uin
             }
         }
     }
+}
+
+// convenience form: bias loaded in place (1-CTA kernel, SwiGLU path)
+template <int ACT, int RES, bool OUT_F32>
+__device__ __forceinline__ void epilogue_chunk32(const GemmParams2& p, const uint32_t (&acc)[32], const uint32_t (&accu)[32],
+                                                 int row, bool row_ok, int col_in, int col_out, int n_out_total) {
+    uint4 b4[4], r4[4];
+    epilogue_load_bias(p, col_in, b4);
+    if (RES == EPI_RES_BF16) epilogue_load_res_bf16(p, row, row_ok, col_out, n_out_total, r4);
+    epilogue_chunk32<ACT, RES, OUT_F32>(p, acc, accu, row, row_ok, col_in, col_out, n_out_total, b4, r4);
 }
 
 }  // namespace gvl

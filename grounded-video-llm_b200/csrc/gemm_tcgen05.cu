@@ -339,11 +339,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, RES, OUT_F32>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0ull;
+    if (first_use_on_device(attr_devs)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return GVL_ERR_CUDA;
-        attr_set = true;
     }
     int grid = p.num_m_tiles * p.num_n_tiles;
     if (grid > num_sms()) grid = num_sms();

@@ -46,8 +46,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// arrive on the leader's tempty barrier. What it orders is this warp's tcgen05.ld of the accumulator stage (completed by
+// tcgen05.wait::ld, fenced by tcgen05.fence::before_thread_sync) against the leader's next tcgen05.mma -- TMEM, not memory -- so
+// the default (.release.cta) form is enough; the .release.cluster form compiled to MEMBAR.ALL.GPU + ERRBAR per tile and warp,
+// ~10 % of the epilogue warps' stall samples in the IV2 fc1 capture (profiles/r2_gemm.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* tmap, uint32_t leader_bar, int c_inner,
                                                 int c_outer) {
@@ -194,14 +198,37 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             const int row = m_idx * 2 * C2_BM + rank * C2_BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * C2_BN;
+            if constexpr (ACT == EPI_ACT_SWIGLU) {
 #pragma unroll 1
-            for (int c = chunk_lo; c < chunk_hi; ++c) {
-                uint32_t acc[32], accu[32];
-                ptx::tmem_ld_32x32(t_row + c * 32, acc);
-                if (ACT == EPI_ACT_SWIGLU) ptx::tmem_ld_32x32(t_row + C2_BN / 2 + c * 32, accu);
-                ptx::tmem_wait_ld();
-                epilogue_chunk32<ACT, RES, OUT_F32>(p, acc, accu, row, row_ok, n_idx * C2_BN + c * 32,
-                                                    n_idx * BN_OUT + c * 32, n_out_total);
+                for (int c = chunk_lo; c < chunk_hi; ++c) {
+                    uint32_t acc[32], accu[32];
+                    ptx::tmem_ld_32x32(t_row + c * 32, acc);
+                    ptx::tmem_ld_32x32(t_row + C2_BN / 2 + c * 32, accu);
+                    ptx::tmem_wait_ld();
+                    epilogue_chunk32<ACT, RES, OUT_F32>(p, acc, accu, row, row_ok, n_idx * C2_BN + c * 32,
+                                                        n_idx * BN_OUT + c * 32, n_out_total);
+                }
+            } else {
+                // software-pipelined: the tcgen05.ld of chunk i+1 is in flight while chunk i goes through the epilogue math and its
+                // global stores (the single-buffered loop spent ~30 % of its stall samples waiting on the TMEM load)
+                uint32_t acc[2][32];
+                uint4 b4[2][4], r4[2][4];
+                ptx::tmem_ld_32x32(t_row + chunk_lo * 32, acc[0]);
+                epilogue_load_bias(p, n_idx * C2_BN + chunk_lo * 32, b4[0]);
+                if (RES == EPI_RES_BF16) epilogue_load_res_bf16(p, row, row_ok, n_idx * BN_OUT + chunk_lo * 32, n_out_total, r4[0]);
+#pragma unroll
+                for (int i = 0; i < CH_PER; ++i) {
+                    const int c = chunk_lo + i;
+                    ptx::tmem_wait_ld();
+                    if (i + 1 < CH_PER) {
+                        ptx::tmem_ld_32x32(t_row + (c + 1) * 32, acc[(i + 1) & 1]);
+                        epilogue_load_bias(p, n_idx * C2_BN + (c + 1) * 32, b4[(i + 1) & 1]);
+                        if (RES == EPI_RES_BF16)
+                            epilogue_load_res_bf16(p, row, row_ok, n_idx * BN_OUT + (c + 1) * 32, n_out_total, r4[(i + 1) & 1]);
+                    }
+                    epilogue_chunk32<ACT, RES, OUT_F32>(p, acc[i & 1], acc[i & 1], row, row_ok, n_idx * C2_BN + c * 32,
+                                                        n_idx * BN_OUT + c * 32, n_out_total, b4[i & 1], r4[i & 1]);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -221,10 +248,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 template <int ACT, int RES, bool OUT_F32>
 int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams2& p, cudaStream_t stream) {
     auto kern = gemm_bf16_tcgen05_2cta_kernel<ACT, RES, OUT_F32>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0ull;
+    if (first_use_on_device(attr_devs)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM) != cudaSuccess) return GVL_ERR_CUDA;
-        attr_set = true;
     }
     int clusters = p.num_m_tiles * p.num_n_tiles;
     if (clusters > num_sms() / 2) clusters = num_sms() / 2;

@@ -22,6 +22,17 @@ extern long long g_launch_count;  // kernels launched by this library (bench.py:
 
 int num_sms();
 
+// Per-kernel "function attributes already set" state is PER DEVICE (cudaFuncSetAttribute applies to the current device's copy of
+// the function): returns true the first time it is called for `mask` on the current device. One 64-bit mask per call site.
+inline bool first_use_on_device(unsigned long long& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // Programmatic dependent launch (PDL) for the decode chain: when g_pdl is set, kernels are launched with
 // programmaticStreamSerialization so that kernel N+1 is scheduled while kernel N drains; every such kernel calls
 // pdl_wait() (griddepcontrol.wait) before it touches anything its predecessor wrote. Weight prefetches are issued

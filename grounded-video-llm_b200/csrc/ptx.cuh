@@ -223,21 +223,24 @@ __device__ __forceinline__ float fast_exp2(float x) {  // one MUFU.EX2; ex2(-inf
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// Exact-erf GELU (nn.GELU default) for a bf16-rounded input, result rounded to bf16 by the caller.
-// erf through Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. ~4 orders of magnitude below one bf16 ulp) in the
-// cancellation-free form  gelu(x) = x>0 ? x - x*q : -|x|*q,  q = 0.5 * poly(t) * exp(-x^2/2),  t = 1/(1 + p|x|/sqrt2):
-// 2 MUFU + ~12 FMA-pipe instructions instead of the ~40-instruction branchy erff() -- ncu showed the IV2 fc1 GEMM
-// epilogue issue-bound on erff (profiles/r1_gemm.md).
+// Exact-erf GELU (nn.GELU default) for a bf16-rounded input, result rounded to bf16 by the caller, in the cancellation-free
+// form   gelu(x) = max(x, 0) - |x| * q,   q = Phi(-|x|) = 0.5 * erfc(|x| / sqrt2) = exp2(P7(min(|x|, 6.5)))
+// (x > 0: x - x q;  x < 0: x q).  P7 = degree-7 fit of log2(0.5 erfc(a / sqrt2)) on [0, 6.5]: relative error of q < 1.4e-5,
+// absolute error of gelu < 6e-7 everywhere (|x| q(6.5) = |x| * 4e-11 beyond the clamp). 1 MUFU + 11 FMA-pipe instructions, no
+// select (a ternary around the polynomial compiles to a divergent branch per element that serialises a 32-element chunk).
+// tools/check_gelu.py checks ALL 65280 finite bf16 inputs against double-precision erfc: no output with |gelu| > 1e-6 is off
+// by more than one bf16 ulp. The Abramowitz-Stegun 7.1.26 form of round 1 cost 2 MUFU + ~19 FMA-pipe instructions and kept the
+// InternVideo2 fc1 GEMM epilogue-bound at 59 % tensor-pipe activity (profiles/r2_gemm.md).
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    const float q = 0.5f * poly * t * fast_exp2(-z * z * 1.4426950408889634f);   // 0.5 * erfc(z)
-    const float xq = x * q;
-    return x > 0.f ? x - xq : xq;
+    const float a = fminf(fabsf(x), 6.5f);
+    float p = fmaf(a, -1.808800448e-06f, 6.107371155e-05f);
+    p = fmaf(a, p, -9.264032706e-04f);
+    p = fmaf(a, p, 8.492015302e-03f);
+    p = fmaf(a, p, -5.392925814e-02f);
+    p = fmaf(a, p, -4.584917128e-01f);
+    p = fmaf(a, p, -1.151243210e+00f);
+    p = fmaf(a, p, -9.999950528e-01f);
+    return fmaf(-fabsf(x), fast_exp2(p), fmaxf(x, 0.f));
 }
 // x * sigmoid(1.702 x) with the reference's three bf16 rounding points (HF QuickGELUActivation on
 // a bf16 tensor: mul -> sigmoid -> mul).

@@ -457,7 +457,8 @@ class LLAVA_NEXT_VIDEO:
         _lib.check(rc, "gvl_visual_concat")
         return out
 
-    def encode_images(self, samples, unit_chunk=48):
+    def _encode_local_units(self, samples, unit_chunk=48):
+        """This rank's block-partition share of the (clip, segment) units -> [units_local, tokens_per_seg, D]."""
         spatial = samples["spatial_pixel_values"]
         temporal = samples["temporal_pixel_values"]
         B, segs = spatial.shape[:2]
@@ -480,8 +481,19 @@ class LLAVA_NEXT_VIDEO:
         else:
             tps = (156 if self.llm == "phi3.5" else 64) + 16 * fps + 1
             local = torch.empty((0, tps, self.language_model.dim), dtype=torch.bfloat16, device=self.device)
-        full = gdist.allgather_units(local, n_units)                # the ONE collective on the path
+        return local, B, segs
+
+    def encode_images(self, samples, unit_chunk=48):
+        """Reference semantics (llava_next_video.py:491-566): every caller gets the full [B, segs*tokens_per_seg, D]."""
+        local, B, segs = self._encode_local_units(samples, unit_chunk)
+        full = gdist.allgather_units(local, B * segs)               # the ONE collective on the path (SURVEY 8e)
         return full.reshape(B, segs * full.shape[1], full.shape[2])
+
+    def encode_images_for_decode(self, samples, unit_chunk=48):
+        """What `generate` needs: only the clips THIS rank decodes (clip b -> rank b % world). Same single collective, as an
+        all-to-all with per-peer splits (gvl.dist.exchange_units). Returns (feats [n_mine, ...], clip indices)."""
+        local, B, segs = self._encode_local_units(samples, unit_chunk)
+        return gdist.exchange_units(local, B, segs)
 
     # ---------------------------------------------------------------- prepare_multimodal_inputs (:568-596)
     def get_input_embeddings(self):
@@ -522,24 +534,23 @@ class LLAVA_NEXT_VIDEO:
             id_lists = [self.tokenizer_image_token(t, self.tokenizer) for t in samples["prompts"]]
             pad_id, eos_id = self.tokenizer.pad_token_id, self.tokenizer.eos_token_id
         ids, mask = hostlogic.left_pad(id_lists, pad_id, self.max_txt_len)
-        feats = self.encode_images(samples)
-        video_ids = samples.get("video_ids", ["video"] * len(id_lists))
-        embeds, _, masks = self.prepare_multimodal_inputs(ids, None, mask, feats, video_ids)
-        B = embeds.shape[0]
-        rank, ws = gdist.world()
-        mine = gdist.clips_for_rank(B, rank, ws)
+        feats, mine = self.encode_images_for_decode(samples)
+        B = len(id_lists)
+        video_ids = samples.get("video_ids", ["video"] * B)
         gk = dict(generate_kwargs)
         gk.setdefault("do_sample", False)
         local = {}
-        for b in mine:
-            local[b] = self.language_model.generate(inputs_embeds=embeds[b:b + 1], attention_mask=masks[b:b + 1],
-                                                    eos_token_id=eos_id, pad_token_id=pad_id, **gk)[0]
+        if mine:
+            sel = torch.tensor(mine, dtype=torch.long)
+            embeds, _, masks = self.prepare_multimodal_inputs(ids[sel], None, mask[sel], feats, [video_ids[b] for b in mine])
+            for i, b in enumerate(mine):
+                local[b] = self.language_model.generate(inputs_embeds=embeds[i:i + 1], attention_mask=masks[i:i + 1],
+                                                        eos_token_id=eos_id, pad_token_id=pad_id, **gk)[0]
+        rank, ws = gdist.world()
         if ws > 1:
-            gathered = gdist.gather_strings({b: t.cpu() for b, t in local.items()})
-            merged = {}
-            for d in gathered:
-                merged.update(d)
-            local = merged
+            width = int(gk.get("max_new_tokens", 16))
+            gathered = gdist.gather_tokens(local, B, width, pad_id if pad_id is not None else 0, self.device)
+            local = dict(enumerate(gathered))
         toks = [local[b] for b in range(B)]
         if self.tokenizer is not None and "input_ids" not in samples:
             text = self.tokenizer.batch_decode([t.cpu().tolist() for t in toks], skip_special_tokens=True)
