@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+    python bench.py --impl reference ...      # the reference's own modules (oracle/_ref) on the host CPU cores
 
 One "step" = one pass of the whole hot path over one batch of synthetic clips (BASELINE.json configs[1] at N=1:
 1 clip = 12 CLIP key-frames 336^2 + 96 frames 224^2 -> 3420 visual tokens -> 3483-token prefill -> 16 greedy tokens).
@@ -103,82 +103,65 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU (reference) arm
-def cpu_reference_sample(threads=None):
-    """The reference's algorithm on the host cores (oracle port, fp32 -- the reference's own CPU mode, BASELINE config 1),
-    timed on a BOUNDED sample of the 96-frame workload and scaled by the layer / unit counts it skips:
-      1 CLIP image x 23 layers (of 12 images), 1 InternVideo2 segment x 2 blocks (of 12 x 39),
-      1 decoder layer prefill at S=3483 (of 32), 1 decoder-layer decode step against a 3483-token cache (of 32 x 16),
-      1 lm_head row. Returns (videos_per_s, seconds_per_video, detail dict)."""
-    import torch
-    from oracle import gvl_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    t = {}
-    with torch.inference_mode():
-        P = O.make_clip_params(seed=1)
-        pix = torch.randn(1, 3, 336, 336)
-        t0 = time.perf_counter()
-        O.clip_hidden_states(pix, P, 16, 24, mode="fp32", upto=23)
-        t["clip_image_23_layers"] = time.perf_counter() - t0
-        del P
-        nb = 2
-        P = O.make_iv2_params(depth=nb + 1, seed=3)
-        pix = torch.randn(1, 3, 8, 224, 224)
-        t0 = time.perf_counter()
-        O.iv2_forward(pix, P, 16, nb + 1, mode="fp32", x_vis_return_idx=-2)     # runs blocks 0..nb-1
-        t["iv2_segment_%d_blocks" % nb] = time.perf_counter() - t0
-        del P
-        P = O.make_lm_params(arch="phi3", layers=1, vocab=32366, seed=7)
-        cfg = dict(arch="phi3", layers=1, heads=32, kv_heads=32, head_dim=96, eps=1e-5, rope=O.phi35_rope_cfg(96))
-        emb = torch.randn(S_PREFILL, 3072) * 0.05
-        t0 = time.perf_counter()
-        _, hidden = O.lm_forward(emb[:, :], dict(P, **{"lm_head.weight": P["lm_head.weight"][:8], "lm_head.bias": P["lm_head.bias"][:8]}),
-                                 cfg, mode="fp32", return_hidden=True)
-        t["lm_prefill_1_layer"] = time.perf_counter() - t0
-        # one KV-cached decode step of one layer (the reference decodes with a cache, modeling_phi3.py:721)
-        x = torch.randn(1, 3072) * 0.05
-        kc, vc = torch.randn(32, S_PREFILL, 96), torch.randn(32, S_PREFILL, 96)
-        pre = "model.layers.0."
-        t0 = time.perf_counter()
-        h = O.rmsnorm(x, P[pre + "input_layernorm.weight"], 1e-5, "fp32")
-        qkv = O.linear(h, P[pre + "self_attn.qkv_proj.weight"], None, "fp32")
-        q = qkv[:, :3072].reshape(1, 32, 96).transpose(0, 1)
-        o = O.attention_core(q[None], kc[None], vc[None], 96 ** -0.5, True, "fp32")[0].transpose(0, 1).reshape(1, 3072)
-        x = x + O.linear(o, P[pre + "self_attn.o_proj.weight"], None, "fp32")
-        h = O.rmsnorm(x, P[pre + "post_attention_layernorm.weight"], 1e-5, "fp32")
-        gate, up = O.linear(h, P[pre + "mlp.gate_up_proj.weight"], None, "fp32").chunk(2, -1)
-        x = x + O.linear(up * torch.nn.functional.silu(gate), P[pre + "mlp.down_proj.weight"], None, "fp32")
-        t["lm_decode_step_1_layer"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.linear(O.rmsnorm(x, P["model.norm.weight"], 1e-5, "fp32"), P["lm_head.weight"], P["lm_head.bias"], "fp32")
-        t["lm_head_1_row"] = time.perf_counter() - t0
-    sec = (12 * t["clip_image_23_layers"] + 12 * 39 / nb * t["iv2_segment_%d_blocks" % nb] + 32 * t["lm_prefill_1_layer"]
-           + t["lm_head_1_row"] + (DECODE_TOKENS - 1) * (32 * t["lm_decode_step_1_layer"] + t["lm_head_1_row"]))
-    return 1.0 / sec, sec, t
+REF_ARM_BUDGET_S = 100.0      # timed samples of the reference arm stop after this much CPU time (the run must end within minutes)
+
+
+def _ref_sampler():
+    """The REFERENCE'S OWN modules on the host cores (oracle/ref_bench.py; kind "reference"): test / measurement infrastructure,
+    the one place besides tests/ and smoke() where bench.py executes anything under oracle/."""
+    from oracle import ref_bench, ref_shims
+    if not ref_shims.available():
+        raise RuntimeError("reference files not installed: run `python -c 'import __graft_entry__ as g; g.build()'` where "
+                           "/root/reference exists (oracle/build_ref.py copies them to the git-ignored oracle/_ref/)")
+    return ref_bench
+
+
+def cpu_reference_sample(sampler=None):
+    """One bounded sample of the configs[1] workload through the reference's stock modules (fp32, all host cores), scaled to the
+    full clip. Returns (videos_per_s, seconds_per_video, detail, sampler)."""
+    rb = _ref_sampler()
+    sampler = sampler or rb.RefCpuSampler()
+    sec, detail = sampler.sample()
+    return 1.0 / sec, sec, detail, sampler
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    rb = _ref_sampler()
     cores = os.cpu_count() or 1
-    vals = []
+    sampler = rb.RefCpuSampler(cores)
+    vals, spent = [], 0.0
     for i in range(args.warmup + args.steps):
-        v, sec, detail = cpu_reference_sample(cores)
+        t0 = time.perf_counter()
+        sec, detail = sampler.sample()
+        spent += time.perf_counter() - t0
         if i >= args.warmup:
-            vals.append((v, sec, detail))
-    v = sum(x[0] for x in vals) / len(vals)
-    sec = sum(x[1] for x in vals) / len(vals)
-    sample = "1 CLIP image x23 layers + 1 IV2 segment x2 blocks + 1 decoder layer prefill S=%d + 1 decoder-layer decode step + " \
-             "1 lm_head row, fp32, scaled to 12 images / 12x39 blocks / 32 layers / %d tokens (extrapolated)" % (S_PREFILL, DECODE_TOKENS)
+            vals.append((sec, detail))
+        if spent > REF_ARM_BUDGET_S and (vals or i + 1 >= args.warmup):
+            if not vals:
+                vals.append((sec, detail))                         # the warm-up alone used the budget: keep its last sample
+            break
+    sec = sum(x[0] for x in vals) / len(vals)
+    v = 1.0 / sec
+    cfg1 = None
+    if os.environ.get("GVL_REF_CFG1", "1") != "0":
+        try:
+            cfg1 = rb.cfg1_end_to_end(cores)
+        except Exception as e:                                     # noqa: BLE001 -- e.g. not enough host memory for the fp32 3.8B decoder
+            cfg1 = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "Phi-3.5-3.8B grounding inference, 1 clip = 96 frames (12x336^2 + 96x224^2), prefill S=%d + %d greedy tokens"
-                                  % (S_PREFILL, DECODE_TOKENS), "where": "host CPU, oracle port of the reference (torch fp32)"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": "BASELINE configs[1]: Phi-3.5-3.8B grounding inference, 1 clip = 96 frames (12x336^2 + 96x224^2), prefill "
+                                  "S=%d + %d greedy tokens" % (S_PREFILL, DECODE_TOKENS),
+                      "where": "host CPU, the reference's own modules (oracle/_ref), torch fp32, %d threads" % cores,
+                      "samples_timed": len(vals), "sample_budget_s": REF_ARM_BUDGET_S},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sampler.SAMPLE},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0, "detail_s": vals[-1][2]}
+           "gpu_launches": 0, "detail_s": vals[-1][1],
+           "extra": {"cfg1_cpu_end_to_end": cfg1}}
     _emit(json.dumps(out))
     return 0
 
@@ -294,10 +277,16 @@ def run_gvl_arm(args):
     for i in range(len(mine)):
         m.language_model.prefill(emb[i], n_new=DECODE_TOKENS)
     ev[2].record()
+    torch.cuda.synchronize()
+    fam = {}
+    for kind, name in ((0, "gemm"), (1, "attn"), (2, "gemv")):     # families of exactly ONE encode + prefill per owned clip
+        ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.gvl_profile_collect(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n))
+        fam[name] = (ms.value, work.value, n.value)
+    lib.gvl_profile_enable(0)
     m.language_model.generate(inputs_embeds=emb[:1], attention_mask=masks[:1], max_new_tokens=DECODE_TOKENS)
     ev[3].record()
     torch.cuda.synchronize()
-    lib.gvl_profile_enable(0)
     for lmh in m.language_model._lms.values():
         lib.gvl_lm_set_graph(lmh, 1)
     # ---- decode roofline: clean (profiling off) prefill vs prefill + 16-token generate on the same embeddings; the
@@ -322,24 +311,22 @@ def run_gvl_arm(args):
     dec_steps = DECODE_TOKENS - 1                                     # the first token comes out of the prefill
     dec_step_ms = (dv[1].elapsed_time(dv[2]) - dv[0].elapsed_time(dv[1])) / dec_steps
     dec_bytes = DECODE_BYTES_WEIGHTS + (emb.shape[1] + dec_steps / 2.0) * KV_BYTES_PER_CTX_TOKEN
-    fam = {}
-    for kind, name in ((0, "gemm"), (1, "attn"), (2, "gemv")):
-        ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-        lib.gvl_profile_collect(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n))
-        fam[name] = (ms.value, work.value, n.value)
     pk = _peaks()
     if rank == 0:
         g_ms, g_fl, g_n = fam["gemm"]
         a_ms, a_fl, a_n = fam["attn"]
         v_ms, v_by, v_n = fam["gemv"]
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-        roof = {"kernel": "gvl::gemm_bf16_tcgen05_kernel (all epilogue variants)", "bound": "tensor", "achieved": ach,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                # dram__bytes_read + dram__bytes_write of ONE captured launch of this family (InternVideo2 fc1, 24588x6144x1408,
-                # profiles/r1_gemm_r1_ncu_metrics.csv; algorithmic 388 MB): constant from the committed ncu capture, not measured live
-                "traffic": 336.0e6, "traffic_launch": "IV2 fc1 24588x6144x1408 (ncu --set full, profiles/r1_gemm.md)",
+        prof_ms = ev[0].elapsed_time(ev[2])                         # one encode_images + one splice/prefill per owned clip
+        # dram__bytes_read + dram__bytes_write of the dominant launch of this family (InternVideo2 fc1, 24588x6144x1408, algorithmic
+        # 388 MB) from the committed `ncu --set full` capture of the SAME kernel (profiles/r2_gemm.md); not measured live
+        roof = {"kernel": "gvl::gemm_bf16_tcgen05_2cta_kernel (cta_group::2, all epilogue variants; the 1-CTA kernel for small shapes)",
+                "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": 337.0e6, "traffic_launch": "IV2 fc1 24588x6144x1408: 88.0 MB read + 249.1 MB written (ncu --set full, "
+                                                       "profiles/r2_gemm_iv2_fc1_ncu_metrics.csv); algorithmic 69 + 17 + 302 MB",
                 "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
-                "share_of_step_ms": g_ms}
+                "share_of_step": g_ms / prof_ms if prof_ms > 0 else None, "family_ms": g_ms, "profiled_region_ms": prof_ms,
+                "profiled_region": "one encode_images + one splice/prefill (per-launch CUDA events on; decode excluded)"}
         enc_ms, pre_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
         per_rank_clips = len(mine)
         prefill_s = (clean_enc_ms + clean_pre_ms) * 1e-3
@@ -366,14 +353,36 @@ def run_gvl_arm(args):
                                     "what": "uint8 clip [96,3,336,336] in pinned host memory -> H2D -> GPU frame_transform (Pillow-bicubic "
                                             "bit-exact resize 336->224, key-frame selection, normalisation) -> generate -> tokens to host"},
             "peaks": pk,
+            "tokens_clip0_sha256_16": tok_sha,
+            "strong_scaling_1_clip_ms": strong_ms,
         }
-    cpu = None
+    # ---- result check across N: sha256 of clip 0's greedy tokens (clip 0 is the same synthetic clip at every N and every
+    # clips-per-gpu: make_clip_inputs draws clips in order from one seeded generator), printed so that N=1 / 2 / 4 / 8 can be compared
+    import hashlib
+    toks0 = one_step(resident, True)[0]
+    tok_sha = hashlib.sha256(",".join(str(int(x)) for x in toks0.tolist()).encode()).hexdigest()[:16]
+    # ---- strong scaling of ONE clip over the N ranks (12 units block-partitioned, decoder on rank 0): latency in ms
+    strong_ms = None
+    if world > 1:
+        one = synth.make_clip_inputs(1, device=dev)
+        for _ in range(2):
+            m.generate(one, max_new_tokens=DECODE_TOKENS)
+        strong_ms = timed(one, False, 3) / 3
+        if rank == 0:
+            t1 = m.generate(one, max_new_tokens=DECODE_TOKENS)[0]
+            assert hashlib.sha256(",".join(str(int(x)) for x in t1.tolist()).encode()).hexdigest()[:16] == tok_sha, \
+                "clip 0 decoded from units encoded on %d ranks differs from the weak-scaling run" % world
+    cpu, gpu_ref = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, detail = cpu_reference_sample()
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "1 CLIP image x23 layers + 1 IV2 segment x2 blocks + 1 decoder layer prefill + 1 decoder-layer decode step "
-                         "+ 1 lm_head row (fp32 oracle port), scaled to the full clip; %.1f s/video extrapolated" % sec,
-               "detail_s": detail}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import gpu_reference
+            gpu_ref = gpu_reference.measure(reps=3, n_new=DECODE_TOKENS)
+        except Exception as e:                                     # noqa: BLE001 -- a baseline leg must not take the bench line down
+            gpu_ref = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        v, sec, detail, sampler = cpu_reference_sample()
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+               "sample": sampler.SAMPLE + "; %.1f s/video" % sec, "detail_s": detail}
     if rank == 0:
         value = B * args.steps / (total_ms * 1e-3)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -390,6 +399,7 @@ def run_gvl_arm(args):
                "e2e": {"value": B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms / args.steps, "api": "gvl.model.LLAVA_NEXT_VIDEO.generate(samples) with pinned host tensors"},
                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "extra": extra}
+        out["extra"]["gpu_reference"] = gpu_ref          # the reference's modules, torch eager + FA2, same GPU (tools/gpu_reference.py)
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
