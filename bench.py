@@ -353,8 +353,6 @@ def run_gvl_arm(args):
                                     "what": "uint8 clip [96,3,336,336] in pinned host memory -> H2D -> GPU frame_transform (Pillow-bicubic "
                                             "bit-exact resize 336->224, key-frame selection, normalisation) -> generate -> tokens to host"},
             "peaks": pk,
-            "tokens_clip0_sha256_16": tok_sha,
-            "strong_scaling_1_clip_ms": strong_ms,
         }
     # ---- result check across N: sha256 of clip 0's greedy tokens (clip 0 is the same synthetic clip at every N and every
     # clips-per-gpu: make_clip_inputs draws clips in order from one seeded generator), printed so that N=1 / 2 / 4 / 8 can be compared
@@ -372,6 +370,9 @@ def run_gvl_arm(args):
             t1 = m.generate(one, max_new_tokens=DECODE_TOKENS)[0]
             assert hashlib.sha256(",".join(str(int(x)) for x in t1.tolist()).encode()).hexdigest()[:16] == tok_sha, \
                 "clip 0 decoded from units encoded on %d ranks differs from the weak-scaling run" % world
+    if rank == 0:
+        extra["tokens_clip0_sha256_16"] = tok_sha
+        extra["strong_scaling_1_clip_ms"] = strong_ms
     cpu, gpu_ref = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

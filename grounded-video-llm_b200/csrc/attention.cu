@@ -271,15 +271,11 @@ int launch_attn(const AttnArgs& a, cudaStream_t stream) {
 int attention_fwd(const AttnArgs& a, cudaStream_t stream) {
     if (a.head_dim % 8 != 0 || a.head_dim > 128 || a.heads % a.kv_heads != 0) return GVL_ERR_ARG;
     if (a.sq <= 0 || a.skv <= 0) return GVL_ERR_ARG;
-    static const bool force_mma = getenv("GVL_ATTN_MMA") != nullptr;   // A/B switch for bring-up / profiling
-    if (!force_mma && attention_tc_supported(a)) {
+    if (attention_tc_supported(a)) {
         prof_begin(GVL_PROF_ATTN, 4.0 * a.batch * a.heads * (double)a.sq * a.skv * a.head_dim * (a.causal ? 0.5 : 1.0), stream);
-        static const bool force_v1 = getenv("GVL_ATTN_V1") != nullptr;
-        // attention_tc3.cu (double-buffered 64-key score tiles, one MMA issuer per query tile) measured equal to
-        // attention_tc2.cu on every production shape (profiles/r1_attention_tc.md): v2 stays the default, GVL_ATTN_V3=1 selects v3
-        static const bool use_v3 = getenv("GVL_ATTN_V3") != nullptr;
-        int rc = (a.sq > 128 && !force_v1) ? (use_v3 ? attention_tc3_fwd(a, stream) : attention_tc2_fwd(a, stream))
-                                           : attention_tc_fwd(a, stream);
+        // two query tiles per CTA (attention_tc2.cu) whenever there is more than one tile of queries; the one-tile kernel
+        // (attention_tc.cu) serves Sq <= 128 (decode-time prefill of short prompts, tests)
+        int rc = a.sq > 128 ? attention_tc2_fwd(a, stream) : attention_tc_fwd(a, stream);
         prof_end(GVL_PROF_ATTN, stream);
         return rc;
     }

@@ -1,8 +1,7 @@
 // Decode-side kernels (q_len = 1): everything here is HBM-bound weight / KV streaming, so the
 // design rules are coalesced 128-bit loads, many bytes in flight per SM and no tensor cores.
-//   gemv_kernel            y = W x for M<=4 rows of x, optional fused input RMSNorm, SwiGLU, residual, bias
+//   (the GEMV lives in gemv.cu)
 //   decode_attn_kernel     one query vs the KV cache, split along the context (flash-decoding style)
-//   decode_attn_combine    merge the per-split (max, sum, partial-output) triples
 //   argmax / token kernels greedy sampling + device-side step bookkeeping (so a step is graph-replayable)
 // Reference call sites: Phi3DecoderLayer.forward with q_len=1 (modeling_phi3.py:1034-1095, 629-775),
 // lm_head + .float() (modeling_phi3.py:1525-1526), HF greedy loop (llava_next_video.py:655-661).
@@ -31,141 +30,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
                  : "l"(p));
     return r;
 }
-__device__ __forceinline__ float dot8(uint4 w, uint4 x) {
-    float2 a, b;
-    float s;
-    a = unpack_bf16(w.x); b = unpack_bf16(x.x); s = a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.y); b = unpack_bf16(x.y); s += a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.z); b = unpack_bf16(x.z); s += a.x * b.x + a.y * b.y;
-    a = unpack_bf16(w.w); b = unpack_bf16(x.w); s += a.x * b.x + a.y * b.y;
-    return s;
-}
 
-#if 0  // first-generation GEMV (kept for reference; superseded by gemv.cu)
-constexpr int GEMV_THREADS = 256;
-constexpr int GEMV_MAXM = 4;
-
-// x rows are staged (and optionally RMS-normalised exactly like rmsnorm_bf16) in shared memory as bf16.
-// Each warp owns whole output rows; SWIGLU pairs the gate row and the up row of one output column.
-template <int MT, bool SWIGLU>
-__global__ void __launch_bounds__(GEMV_THREADS)
-gemv_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ W, int ldw,
-            void* __restrict__ out, int ldo, int N, int K, const __nv_bfloat16* __restrict__ norm_w, float eps,
-            const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, int ldr,
-            int out_f32) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem);  // [MT][K]
-    __shared__ float s_red[MT][GEMV_THREADS / 32];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kv = K / 8;
-
-    // ---- stage x (with optional RMSNorm)
-    float ss[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) ss[m] = 0.f;
-    for (int i = tid; i < kv; i += GEMV_THREADS) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            uint4 v = *(reinterpret_cast<const uint4*>(x + (size_t)m * ldx) + i);
-            reinterpret_cast<uint4*>(sx + (size_t)m * K)[i] = v;
-            if (norm_w != nullptr) {
-                float2 f;
-                f = unpack_bf16(v.x); ss[m] += f.x * f.x + f.y * f.y;
-                f = unpack_bf16(v.y); ss[m] += f.x * f.x + f.y * f.y;
-                f = unpack_bf16(v.z); ss[m] += f.x * f.x + f.y * f.y;
-                f = unpack_bf16(v.w); ss[m] += f.x * f.x + f.y * f.y;
-            }
-        }
-    }
-    if (norm_w != nullptr) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            float v = warp_sum(ss[m]);
-            if (lane == 0) s_red[m][warp] = v;
-        }
-        __syncthreads();
-        float rstd[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < GEMV_THREADS / 32; ++w) t += s_red[m][w];
-            rstd[m] = rsqrtf(t / K + eps);
-        }
-        for (int i = tid; i < kv; i += GEMV_THREADS) {
-            uint4 wv = __ldg(reinterpret_cast<const uint4*>(norm_w) + i);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                uint4 v = reinterpret_cast<uint4*>(sx + (size_t)m * K)[i], o;
-                float2 f, g;
-                f = unpack_bf16(v.x); g = unpack_bf16(wv.x); o.x = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
-                f = unpack_bf16(v.y); g = unpack_bf16(wv.y); o.y = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
-                f = unpack_bf16(v.z); g = unpack_bf16(wv.z); o.z = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
-                f = unpack_bf16(v.w); g = unpack_bf16(wv.w); o.w = pack_bf16(bf16r(f.x * rstd[m]) * g.x, bf16r(f.y * rstd[m]) * g.y);
-                reinterpret_cast<uint4*>(sx + (size_t)m * K)[i] = o;
-            }
-        }
-    }
-    __syncthreads();
-
-    const int n_out = SWIGLU ? N / 2 : N;
-    const int gw = blockIdx.x * (GEMV_THREADS / 32) + warp;
-    const int nw = gridDim.x * (GEMV_THREADS / 32);
-    // two weight rows in flight per warp iteration (SWIGLU: gate row + up row of the same output)
-    for (int o0 = gw * 2; o0 < (SWIGLU ? n_out * 2 : n_out); o0 += nw * 2) {
-        int r0, r1, oc0, oc1;
-        if (SWIGLU) {
-            const int oc = o0 / 2;  // output column
-            oc0 = oc1 = oc;
-            r0 = (oc / 128) * 256 + (oc % 128);  // gate row (interleaved per 256-row block)
-            r1 = r0 + 128;                       // up row
-        } else {
-            oc0 = o0; oc1 = o0 + 1;
-            r0 = o0; r1 = (o0 + 1 < N) ? o0 + 1 : o0;
-        }
-        const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)r0 * ldw);
-        const uint4* w1 = reinterpret_cast<const uint4*>(W + (size_t)r1 * ldw);
-        float a0[MT], a1[MT];
-#pragma unroll
-        for (int m = 0; m < MT; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
-#pragma unroll 4
-        for (int i = lane; i < kv; i += 32) {
-            uint4 v0 = ldg_stream(w0 + i), v1 = ldg_stream(w1 + i);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                uint4 xv = reinterpret_cast<const uint4*>(sx + (size_t)m * K)[i];
-                a0[m] += dot8(v0, xv);
-                a1[m] += dot8(v1, xv);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < MT; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
-        if (lane == 0) {
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                if (SWIGLU) {
-                    const float g = bf16r(a0[m]), u = bf16r(a1[m]);
-                    const float y = u * bf16r(silu_f(g));
-                    reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + oc0] = __float2bfloat16_rn(y);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int oc = j == 0 ? oc0 : oc1;
-                        if (oc >= N || (j == 1 && oc1 == oc0)) continue;
-                        float y = j == 0 ? a0[m] : a1[m];
-                        if (bias) y += __bfloat162float(bias[oc]);
-                        y = bf16r(y);
-                        if (residual) y = bf16r(y + __bfloat162float(residual[(size_t)m * ldr + oc]));
-                        if (out_f32) reinterpret_cast<float*>(out)[(size_t)m * ldo + oc] = y;
-                        else reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + oc] = __float2bfloat16_rn(y);
-                    }
-                }
-            }
-        }
-    }
-}
-
-#endif
 
 // ---------------------------------------------------------------- decode attention
 constexpr int DA_THREADS = 128;
@@ -340,25 +205,6 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     da_finish<D>(ws, counters, o_out, h, nsplit, tid);
 }
 
-// grid = heads, block = D threads
-__global__ void decode_attn_combine(const float* __restrict__ ws, __nv_bfloat16* __restrict__ o, int nsplit, int D) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int h = blockIdx.x, d = threadIdx.x;
-    const float* base = ws + (size_t)h * nsplit * (D + 2);
-    float M = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, base[(size_t)s * (D + 2)]);
-    float num = 0.f, den = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const float* r = base + (size_t)s * (D + 2);
-        if (r[0] == -INFINITY) continue;
-        const float wgt = __expf(r[0] - M);
-        num += wgt * r[2 + d];
-        den += wgt * r[1];
-    }
-    o[(size_t)h * D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
-}
-
 // ---------------------------------------------------------------- greedy sampling / step state
 // first maximal index (torch.argmax tie order); single CTA.
 __global__ void __launch_bounds__(1024)
@@ -492,42 +338,7 @@ step_end_kernel(const float* __restrict__ logits, int n, DecodeState* st, long l
 
 }  // namespace
 
-#if 0  // superseded by gemv.cu
-int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, void* out, int ldo, int M, int N,
-              int K, const __nv_bfloat16* norm_w, float eps, const __nv_bfloat16* bias,
-              const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s) {
-    if (M < 1 || M > GEMV_MAXM || K % 256 != 0 || (act != 0 && act != 3)) return GVL_ERR_ARG;
-    if (act == 3 && N % 256 != 0) return GVL_ERR_ARG;
-    const size_t smem = (size_t)M * K * 2;
-    prof_begin(GVL_PROF_GEMV, 2.0 * (double)N * K, s);  // algorithmic bytes: the weight matrix, read once
-    const int rows = act == 3 ? N / 2 : (N + 1) / 2;  // warp work items
-    int grid = num_sms() * 2;
-    const int need = (rows + GEMV_THREADS / 32 - 1) / (GEMV_THREADS / 32);
-    if (grid > need) grid = need;
-#define GEMV_LAUNCH(MT, SW)                                                                                   \
-    do {                                                                                                      \
-        auto kern = gemv_kernel<MT, SW>;                                                                      \
-        static size_t max_set = 0;                                                                            \
-        if (smem > 48 * 1024 && smem > max_set) {                                                             \
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-                return GVL_ERR_CUDA;                                                                          \
-            max_set = smem;                                                                                   \
-        }                                                                                                     \
-        kern<<<grid, GEMV_THREADS, smem, s>>>(x, ldx, W, ldw, out, ldo, N, K, norm_w, eps, bias, residual, ldr, out_f32); \
-    } while (0)
-    if (act == 3) {
-        switch (M) { case 1: GEMV_LAUNCH(1, true); break; case 2: GEMV_LAUNCH(2, true); break;
-                     case 3: GEMV_LAUNCH(3, true); break; default: GEMV_LAUNCH(4, true); break; }
-    } else {
-        switch (M) { case 1: GEMV_LAUNCH(1, false); break; case 2: GEMV_LAUNCH(2, false); break;
-                     case 3: GEMV_LAUNCH(3, false); break; default: GEMV_LAUNCH(4, false); break; }
-    }
-#undef GEMV_LAUNCH
-    prof_end(GVL_PROF_GEMV, s);
-    g_launch_count++;
-    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
-}
-#endif
+
 
 // workspace: [heads][nsplit][D+2] fp32 partials followed by [heads] int32 arrival counters.
 // The counters must be ZERO before the first call (gvl_lm_create memsets them; they reset themselves afterwards).

@@ -15,9 +15,6 @@ struct DecodeState {
 int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, void* out, int ldo, int M, int N,
               int K, const __nv_bfloat16* norm_w, float eps, const __nv_bfloat16* bias,
               const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s);
-int gemv_bulk_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, void* out, int ldo, int M, int N,
-                   int K, const __nv_bfloat16* norm_w, float eps, const __nv_bfloat16* bias,
-                   const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s);
 size_t decode_attention_workspace(int heads, int head_dim, int max_ctx);
 int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv_bfloat16* vc, __nv_bfloat16* o,
                      float* ws, const int* ctx_len_dev, int heads, int kv_heads, int head_dim, int max_ctx,

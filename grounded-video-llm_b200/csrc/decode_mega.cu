@@ -40,12 +40,16 @@ namespace gvl {
 namespace {
 
 constexpr int MG_CONSUMERS = 8;
-constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 2);          // 8 consumer warps, ring producer, L2 prefetcher
+constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 1);          // 8 consumer warps + the ring producer warp
 constexpr int MG_SLOT_BYTES = MEGA_ROWS * MEGA_SEG * 2;          // 8192: one packed item
 constexpr int MG_SLOTS = 3;                                      // ring depth per consumer warp
 constexpr int MG_RING_BYTES = MG_CONSUMERS * MG_SLOTS * MG_SLOT_BYTES;   // 196608
 constexpr int MG_SMEM_LIMIT = 232448 - 2048;                     // 227 KB opt-in minus static shared memory
 constexpr int MG_ATT_SHORT = 128;                                // ctx <= this: one warp per head
+// bulk copies each producer lane keeps outstanding: 1 while its phase is still ahead of the consumers (pure prefetch: tools/probe_exchange.cu
+// measured 8-22 us per grid-wide exchange with 2-3 copies per lane queued against 4 us with one), all slots once the consumers wait for
+// exactly these items (round-1 sweep of (ahead, current): (1,1) 2.50 (1,2) 2.57 (1,3) 2.52 (2,3) 2.47 ms / step)
+constexpr int MG_INFLIGHT_AHEAD = 1, MG_INFLIGHT_CUR = MG_SLOTS;
 
 __host__ __device__ inline int att_warp_len(int ctx, int H, int G) {
     if (ctx <= MG_ATT_SHORT) return ctx;
@@ -66,9 +70,6 @@ __device__ __forceinline__ void bulk_g2s_m(uint32_t dst, const void* src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
-}
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
     uint32_t ok;
@@ -92,13 +93,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ uint4 ldg_stream4(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -112,22 +106,14 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 }
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 consumer threads
 
-// consumers-only grid barrier
-// `epoch` counts phase boundaries (published for the producer warp), `bars` counts the REAL grid barriers among them (in the
-// flags-in-data mode most boundaries are phase_end() below)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, unsigned& bars, int tid,
-                                             volatile unsigned* cta_epoch, int ablate = 0) {
+// consumers-only grid barrier; `epoch` counts the barriers passed and is published for the producer warp
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch, int tid, volatile unsigned* cta_epoch) {
     cbar();
     ++epoch;
-    if (ablate & 1) {                                // timing ablation only (results are wrong)
-        if (tid == 0) *cta_epoch = epoch;
-        return;
-    }
-    ++bars;
     if (tid == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        const unsigned target = bars * gridDim.x;
+        const unsigned target = epoch * gridDim.x;
         if (ld_acquire_u32(counter) < target) {
             const long long t0 = clock64();
             while (ld_acquire_u32(counter) < target) {
@@ -141,56 +127,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
         *cta_epoch = epoch;                          // the producer warp gates its K / V stream on this (produce_attention)
     }
     cbar();
-}
-// flags-in-data mode: a phase boundary without a grid barrier (the next phase polls its inputs)
-__device__ __forceinline__ void phase_end(unsigned& epoch, int tid, volatile unsigned* cta_epoch) {
-    cbar();
-    ++epoch;
-    if (tid == 0) {
-        __threadfence_block();
-        *cta_epoch = epoch;
-    }
-}
-
-// ------------------------------------------------------------------ flags-in-data packets
-__device__ __forceinline__ uint4 ld_poll4(const void* p) {          // L1-bypassing, never hoisted out of a polling loop
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ uint2 ld_poll2(const void* p) {
-    uint2 r;
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ void st_packet2(uint2* p, uint32_t data, uint32_t flag) {
-    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(data), "r"(flag) : "memory");
-}
-__device__ __forceinline__ void st_packet4(uint4* p, float a, float b, float c, uint32_t flag) {
-    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
-                 "r"(__float_as_uint(c)), "r"(flag) : "memory");
-}
-struct PollGuard {                                                  // a producer died or the phase ids are out of step: trap, never hang
-    long long t0;
-    __device__ __forceinline__ PollGuard() : t0(0) {}
-    __device__ __forceinline__ void spin(const char* what, unsigned want, unsigned got) {
-        if (t0 == 0) { t0 = clock64(); __nanosleep(200); return; }
-        __nanosleep(400);                                           // 38k threads poll: keep the request rate off the weight stream
-        if (clock64() - t0 > 4000000000LL) {
-            printf("gvl: decode_mega %s poll timeout block %d thread %d want %u got %u\n", what, blockIdx.x, threadIdx.x, want, got);
-            __trap();
-        }
-    }
-};
-// 4 consecutive elements (two packets) of an LL vector, polled until both carry `flag`; returns the 4 bf16 as (lo pair, hi pair)
-__device__ __forceinline__ uint2 poll_vec4(const uint2* v, int idx4, unsigned flag, const char* what) {
-    PollGuard g;
-    uint4 r = ld_poll4(v + (size_t)idx4 * 2);
-    while (r.y != flag || r.w != flag) {
-        g.spin(what, flag, r.y != flag ? r.y : r.w);
-        r = ld_poll4(v + (size_t)idx4 * 2);
-    }
-    return make_uint2(r.x, r.z);
 }
 
 // optional per-CTA phase trace (clock64 at: x staged / work done / barrier passed), MegaPlan::trace != nullptr
@@ -299,136 +235,6 @@ __device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat1
     cbar();
 }
 
-// ------------------------------------------------------------------ x staging from {2 x bf16, flag} packets (+ RMSNorm): the poll IS the load
-__device__ __noinline__ void stage_x_ll(const MegaOp& op, unsigned flag, const Smem& S, int tid, int warp, int lane) {
-    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
-    const int nq = op.K / 4;                                       // 4 elements per thread-load; K <= 8192 -> <= 8 per thread
-    uint2 nw[8];
-    if (op.norm_w != nullptr) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (tid + u * 256 < nq) nw[u] = __ldg(reinterpret_cast<const uint2*>(op.norm_w) + tid + u * 256);
-    }
-    // 38k threads re-polling every packet they need put more requests on the L2 than the weight stream itself: only warp 0
-    // waits, on 32 sentinel packets spread over the vector (32 different producer CTAs), everybody else sleeps at the CTA barrier;
-    // afterwards every thread loads its packets once, still verifying the flags (a late packet is re-polled individually)
-    if (warp == 0) {
-        PollGuard g;
-        const uint2* sp = op.x_ll + (size_t)(lane * (nq / 32)) * 2;
-        uint4 r = ld_poll4(sp);
-        while (!__all_sync(0xffffffffu, r.y == flag && r.w == flag)) {
-            g.spin("x sentinel", flag, r.y);
-            r = ld_poll4(sp);
-        }
-    }
-    cbar();
-    // all of this thread's packet loads are issued before the first flag is examined (one L2 round trip for the whole vector when
-    // the data is there; a per-packet poll loop would serialise up to 8 round trips); late packets are re-polled individually
-    uint4 raw[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-        if (tid + u * 256 < nq) raw[u] = ld_poll4(op.x_ll + (size_t)(tid + u * 256) * 2);
-    uint2 xv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-        if (tid + u * 256 < nq) {
-            PollGuard g;
-            while (raw[u].y != flag || raw[u].w != flag) {
-                g.spin("x", flag, raw[u].y != flag ? raw[u].y : raw[u].w);
-                raw[u] = ld_poll4(op.x_ll + (size_t)(tid + u * 256) * 2);
-            }
-            xv[u] = make_uint2(raw[u].x, raw[u].z);
-        }
-    if (op.norm_w == nullptr) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (tid + u * 256 < nq) reinterpret_cast<uint2*>(sx)[tid + u * 256] = xv[u];
-        cbar();
-        return;
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-        if (tid + u * 256 < nq) {
-            float2 f;
-            f = unpack_bf16(xv[u].x); ss += f.x * f.x + f.y * f.y;
-            f = unpack_bf16(xv[u].y); ss += f.x * f.x + f.y * f.y;
-        }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) S.red[warp] = ss;
-    cbar();
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
-    const float rstd = rsqrtf(t / op.K + op.eps);
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-        if (tid + u * 256 < nq) {
-            float2 f, g;
-            uint2 o;
-            f = unpack_bf16(xv[u].x); g = unpack_bf16(nw[u].x); o.x = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            f = unpack_bf16(xv[u].y); g = unpack_bf16(nw[u].y); o.y = pack_bf16(bf16r(f.x * rstd) * g.x, bf16r(f.y * rstd) * g.y);
-            reinterpret_cast<uint2*>(sx)[tid + u * 256] = o;
-        }
-    cbar();
-}
-
-// merge of the split-KV partials from {3 floats, flag} packets: task (head, l) owns dims l, l + 32, l + 64 of that head
-__device__ __noinline__ void stage_x_attn_ll(const MegaPlan& P, unsigned flag, const Smem& S, int ctx, int tid) {
-    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
-    const int D = P.head_dim, H = P.heads, maxp = P.att_maxp;
-    const int Lc = att_warp_len(ctx, H, gridDim.x) * MG_CONSUMERS;
-    if (tid < 32) {                                                 // sentinels: the (m, l) packet of every partial, one head per lane
-        for (int h = tid; h < H; h += 32) {
-            const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
-            for (int s = 0; s <= c1 - c0; ++s) {
-                PollGuard g;
-                const uint4* sp = P.att_ll + ((size_t)h * maxp + s) * 33 + 32;
-                uint4 r = ld_poll4(sp);
-                while (r.w != flag) { g.spin("att sentinel", flag, r.w); r = ld_poll4(sp); }
-            }
-        }
-    }
-    cbar();
-    for (int task = tid; task < H * 32; task += 256) {
-        const int h = task >> 5, l = task & 31;
-        const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
-        const int np = c1 - c0 + 1;
-        const uint4* base = P.att_ll + (size_t)h * maxp * 33;
-        // all partials of the head in flight at once (np <= 8 in this mode), re-polled individually until complete
-        uint4 hd[8], ov[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < np) { hd[j] = ld_poll4(base + (size_t)j * 33 + 32); ov[j] = ld_poll4(base + (size_t)j * 33 + l); }
-        float M = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < np) {
-                PollGuard g;
-                while (hd[j].w != flag || ov[j].w != flag) {
-                    g.spin("att", flag, hd[j].w != flag ? hd[j].w : ov[j].w);
-                    hd[j] = ld_poll4(base + (size_t)j * 33 + 32);
-                    ov[j] = ld_poll4(base + (size_t)j * 33 + l);
-                }
-                M = fmaxf(M, __uint_as_float(hd[j].x));
-            }
-        float den = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < np) {
-                const float w = __expf(__uint_as_float(hd[j].x) - M);
-                den += w * __uint_as_float(hd[j].y);
-                n0 += w * __uint_as_float(ov[j].x); n1 += w * __uint_as_float(ov[j].y); n2 += w * __uint_as_float(ov[j].z);
-            }
-        const float inv = den > 0.f ? 1.0f / den : 0.f;
-        sx[h * D + l] = __float2bfloat16_rn(n0 * inv);
-        if (l + 32 < D) sx[h * D + l + 32] = __float2bfloat16_rn(n1 * inv);
-        if (l + 64 < D) sx[h * D + l + 64] = __float2bfloat16_rn(n2 * inv);
-    }
-    cbar();
-}
-
 // ------------------------------------------------------------------ x staging: merge of the split-KV attention partials
 __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid) {
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
@@ -485,10 +291,9 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
 }
 
 // ------------------------------------------------------------------ consumer side of one GEMV phase (x already staged)
-template <bool LL>
 __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, const __nv_bfloat16* emb_row,
                                            float* extra_out, const Smem& S, uint32_t& cnt, int tid, int warp, int lane,
-                                           long long* occ = nullptr, unsigned out_flag = 0u) {
+                                           long long* occ = nullptr) {
     const int G = gridDim.x, c = blockIdx.x;
     const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
     const int nsel = op.act == 3 ? 2 : 1;
@@ -498,16 +303,8 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     const int g = lane >> 2, t = lane & 3;
     const int nchunk2 = op.seg_len / 64;
     // residual of this thread's output column: loaded now, used in the epilogue (hides one L2 round trip)
-    constexpr bool ll = LL;
-    const bool res_is_ll = ll && !(op.from_embed & 2) && op.res_ll != nullptr;
-    const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : (res_is_ll ? reinterpret_cast<const __nv_bfloat16*>(op.res_ll) : op.residual);
-    // element n of a residual vector: plain bf16, or the data half of its {2 x bf16, flag} packet (this CTA polled the whole vector
-    // when it staged the phase that consumed it, so no flag check here)
+    const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : op.residual;
     auto load_res = [&](int n) -> float {
-        if (res_is_ll) {
-            const uint32_t d = __ldcg(reinterpret_cast<const unsigned int*>(op.res_ll + (n >> 1)));
-            return __uint_as_float((n & 1) ? (d & 0xffff0000u) : (d << 16));
-        }
         return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
     };
     float res_pre = 0.f;
@@ -526,86 +323,87 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     }
     const uint32_t ring_w = ptx::smem_u32(S.ring) + warp * (MG_SLOTS * MG_SLOT_BYTES) + g * 64 + t * 16;   // item: [chunk][row g][64 B]
     const uint32_t x_u32 = ptx::smem_u32(S.xa) + t * 16;
-    for (int q = warp; q < n_items; q += MG_CONSUMERS) {
-        const uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
-        ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
-        const int j = q / ipu, r = q - j * ipu;
-        const int seg = r % nseg;
-        uint32_t wa = ring_w + slot * MG_SLOT_BYTES;
-        uint32_t xa = x_u32 + seg * op.seg_len * 2;
-        float acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-#pragma unroll 2
-        for (int ch = 0; ch < ((P.ablate & 8) ? 0 : nchunk2); ++ch) {
-            const uint4 w0 = lds128(wa), x0 = lds128(xa);
-            const uint4 w1 = lds128(wa + 512), x1 = lds128(xa + 64);
-            mma16816(acc[0], x0.x, x0.x, x0.y, x0.y, w0.x, w0.y);
-            mma16816(acc[1], x0.z, x0.z, x0.w, x0.w, w0.z, w0.w);
-            mma16816(acc[2], x1.x, x1.x, x1.y, x1.y, w1.x, w1.y);
-            mma16816(acc[3], x1.z, x1.z, x1.w, x1.w, w1.z, w1.w);
-            wa += 1024;
-            xa += 128;
-        }
-        if (g == 0) {
-            float2 o;
-            o.x = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-            o.y = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-            *reinterpret_cast<float2*>(S.part + (size_t)q * 8 + 2 * t) = o;
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
-        ++cnt;
+    // The per-item partial sums of a CTA's units usually fit the `part` buffer at once (one pass). A phase whose item count exceeds it
+    // (Llama-3's 128558-row lm_head: 109 units x 8 segments per CTA) runs in passes of `upp` units; upp * ipu is a multiple of 8, so
+    // item q still belongs to warp q % 8, which is the order the producer lane of that warp streams them in.
+    int upp = nu;
+    if (n_items > P.part_items) {
+        const int mult = 8 / ((ipu & 1) ? 1 : (ipu & 2) ? 2 : (ipu & 4) ? 4 : 8);      // 8 / gcd(ipu, 8)
+        upp = (P.part_items / ipu) / mult * mult;
     }
-    cbar();
-    // ---- epilogue: one thread per output column, segments summed in a fixed order
     unsigned long long key = 0ull;
-    const bool out_ll = ll && op.out_ll != nullptr;
-    for (int o0 = 0; o0 < nu * MEGA_ROWS; o0 += 256) {           // warp-uniform trip count: the packet store pairs lanes
-        const int o = o0 + tid;
-        const bool active = o < nu * MEGA_ROWS;
-        const int j = o >> 3, col = o & 7;
-        const int n = (c + j * G) * MEGA_ROWS + col;
-        const bool live = active && n < op.n_out;
-        unsigned short ybits = 0;
-        if (live) {
-            const float* pp = S.part + (size_t)j * ipu * 8 + col;
-            float a0 = 0.f;
-            for (int s = 0; s < nseg; ++s) a0 += pp[s * 8];
-            if (op.act == 3) {
-                float a1 = 0.f;
-                for (int s = 0; s < nseg; ++s) a1 += pp[(nseg + s) * 8];
-                const float gt = bf16r(a0), u = bf16r(a1);
-                const __nv_bfloat16 yv = __float2bfloat16_rn(u * bf16r(silu_f(gt)));
-                ybits = __bfloat16_as_ushort(yv);
-                if (!out_ll) reinterpret_cast<__nv_bfloat16*>(op.out)[n] = yv;
-            } else {
-                float y = a0;
-                if (op.bias) y += __bfloat162float(op.bias[n]);
-                y = bf16r(y);
-                if (res) {
-                    const float rv = o < 256 ? res_pre : load_res(n);
-                    y = bf16r(y + rv);
-                }
-                ybits = __bfloat16_as_ushort(__float2bfloat16_rn(y));
-                if (!out_ll) {
+    for (int u0 = 0; u0 < nu; u0 += upp) {
+        const int nu_p = min(upp, nu - u0);
+        const int q_lo = u0 * ipu, q_hi = (u0 + nu_p) * ipu;
+        for (int q = q_lo + warp; q < q_hi; q += MG_CONSUMERS) {
+            const uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+            const int j = q / ipu, r = q - j * ipu;
+            const int seg = r % nseg;
+            uint32_t wa = ring_w + slot * MG_SLOT_BYTES;
+            uint32_t xa = x_u32 + seg * op.seg_len * 2;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+#pragma unroll 2
+            for (int ch = 0; ch < nchunk2; ++ch) {
+                const uint4 w0 = lds128(wa), x0 = lds128(xa);
+                const uint4 w1 = lds128(wa + 512), x1 = lds128(xa + 64);
+                mma16816(acc[0], x0.x, x0.x, x0.y, x0.y, w0.x, w0.y);
+                mma16816(acc[1], x0.z, x0.z, x0.w, x0.w, w0.z, w0.w);
+                mma16816(acc[2], x1.x, x1.x, x1.y, x1.y, w1.x, w1.y);
+                mma16816(acc[3], x1.z, x1.z, x1.w, x1.w, w1.z, w1.w);
+                wa += 1024;
+                xa += 128;
+            }
+            if (g == 0) {
+                float2 o;
+                o.x = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+                o.y = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+                *reinterpret_cast<float2*>(S.part + (size_t)(q - q_lo) * 8 + 2 * t) = o;
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
+            ++cnt;
+        }
+        cbar();
+        // ---- epilogue of this pass: one thread per output column, segments summed in a fixed order
+        for (int o0 = 0; o0 < nu_p * MEGA_ROWS; o0 += 256) {
+            const int o = o0 + tid;
+            const bool active = o < nu_p * MEGA_ROWS;
+            const int jl = o >> 3, col = o & 7;
+            const int n = (c + (u0 + jl) * G) * MEGA_ROWS + col;
+            const bool live = active && n < op.n_out;
+            if (live) {
+                const float* pp = S.part + (size_t)jl * ipu * 8 + col;
+                float a0 = 0.f;
+                for (int s = 0; s < nseg; ++s) a0 += pp[s * 8];
+                if (op.act == 3) {
+                    float a1 = 0.f;
+                    for (int s = 0; s < nseg; ++s) a1 += pp[(nseg + s) * 8];
+                    const float gt = bf16r(a0), u = bf16r(a1);
+                    reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(u * bf16r(silu_f(gt)));
+                } else {
+                    float y = a0;
+                    if (op.bias) y += __bfloat162float(op.bias[n]);
+                    y = bf16r(y);
+                    if (res) {
+                        const float rv = (u0 == 0 && o < 256) ? res_pre : load_res(n);
+                        y = bf16r(y + rv);
+                    }
                     if (op.out_f32) reinterpret_cast<float*>(op.out)[n] = y;
                     else reinterpret_cast<__nv_bfloat16*>(op.out)[n] = __float2bfloat16_rn(y);
-                }
-                if (extra_out) extra_out[n] = y;
-                if (op.argmax) {
-                    uint32_t u = __float_as_uint(y);
-                    u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-                    const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
-                    key = k > key ? k : key;
+                    if (extra_out) extra_out[n] = y;
+                    if (op.argmax) {
+                        uint32_t u = __float_as_uint(y);
+                        u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+                        const unsigned long long k = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)n);
+                        key = k > key ? k : key;
+                    }
                 }
             }
         }
-        if (out_ll) {
-            // columns n, n + 1 (n even) of one 8-row unit sit in adjacent lanes: one 8-byte {2 x bf16, phase id} packet
-            const unsigned hi = __shfl_down_sync(0xffffffffu, (unsigned)ybits, 1);
-            if (live && !(col & 1)) st_packet2(op.out_ll + (n >> 1), (unsigned)ybits | (hi << 16), out_flag);
-        }
+        if (u0 + upp < nu) cbar();                       // the next pass overwrites the partial sums
     }
     if (op.argmax) {
 #pragma unroll
@@ -618,23 +416,15 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
 }
 
 // ------------------------------------------------------------------ producer side of one GEMV phase: lane w feeds warp w
-__device__ __forceinline__ int cta_items(const MegaOp& op) {
-    const int G = gridDim.x, c = blockIdx.x;
-    const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
-    return nu * (op.act == 3 ? 2 : 1) * op.nseg;
-}
-
 // `inflight` copies per lane while the phase is still ahead of the consumers (pure prefetch: deep queues only delay the
 // latency-critical loads of the phase boundary the consumers are in), `inflight_cur` once the consumers have reached
 // this phase (cta_epoch >= my_epoch) and are waiting for exactly these items.
 __device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, uint32_t& pc, int inflight, int inflight_cur,
-                                              volatile unsigned* cta_epoch, unsigned my_epoch, int lane,
-                                              volatile unsigned* prod_ord, unsigned ord_base) {
+                                              volatile unsigned* cta_epoch, unsigned my_epoch, int lane) {
     const int G = gridDim.x, c = blockIdx.x;
     const int nu = op.units > c ? (op.units - c + G - 1) / G : 0;
     const int ipu = (op.act == 3 ? 2 : 1) * op.nseg;
     const int n_items = nu * ipu;
-    if (lane == 0) *prod_ord = ord_base;               // progress in this CTA's item order, read by the L2 prefetcher
     const uint32_t item_bytes = (uint32_t)op.seg_len * 2 * MEGA_ROWS;
     const int my_n = (lane < MG_CONSUMERS && n_items > lane) ? (n_items - lane + MG_CONSUMERS - 1) / MG_CONSUMERS : 0;
     const uint32_t ring_w = ptx::smem_u32(S.ring) + lane * (MG_SLOTS * MG_SLOT_BYTES);
@@ -660,61 +450,9 @@ __device__ __forceinline__ void produce_phase(const MegaOp& op, const Smem& S, u
                 ++pc;
                 ++m;
                 issued = true;
-                if (lane == 0) *prod_ord = ord_base + (unsigned)m * MG_CONSUMERS;
             }
         }
         if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
-    }
-}
-
-// ------------------------------------------------------------------ L2 prefetcher (10th warp)
-// The rings hold 28 MB, i.e. ~4 us of HBM stream, but a phase boundary (epilogue stores -> grid barrier -> activation
-// staging) lasts longer than that, so with the rings alone HBM idles at every boundary. This warp walks the same item
-// order as the producer and issues cp.async.bulk.prefetch.L2 for items up to `win` items (8 KB each) ahead of it: HBM ->
-// L2 keeps streaming while the rings are full, and after the boundary the ring refills from L2 instead of HBM.
-__device__ __forceinline__ void pf_throttle(volatile unsigned* prod_ord, unsigned my_ord, int win) {
-    while ((int)(my_ord - *prod_ord) > win) __nanosleep(200);
-}
-__device__ __forceinline__ void prefetch_phase(const MegaOp& op, volatile unsigned* prod_ord, unsigned ord_base, int win, int lane) {
-    const int G = gridDim.x, c = blockIdx.x;
-    const int ipu = (op.act == 3 ? 2 : 1) * op.nseg;
-    const int n_items = cta_items(op);
-    const uint32_t item_bytes = (uint32_t)op.seg_len * 2 * MEGA_ROWS;
-    for (int q0 = 0; q0 < n_items; q0 += 32) {
-        if ((int)(ord_base + q0 + 32 - *prod_ord) <= 0) continue;      // the producer is already past this batch
-        pf_throttle(prod_ord, ord_base + q0, win);
-        const int q = q0 + lane;
-        if (q < n_items) {
-            const int j = q / ipu, r = q - j * ipu;
-            const size_t item = (size_t)(c + j * G) * ipu + r;
-            l2_prefetch(reinterpret_cast<const uint8_t*>(op.W) + item * item_bytes, item_bytes);
-        }
-    }
-}
-template <int D>
-__device__ __forceinline__ void prefetch_attention(const MegaPlan& P, int layer, int pos, volatile unsigned* prod_ord,
-                                                   unsigned ord_base, int win, int lane) {
-    pf_throttle(prod_ord, ord_base, win);
-    if (lane >= MG_CONSUMERS) return;
-    const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
-    const int ctx = pos + 1;
-    const int Lw = att_warp_len(ctx, H, gridDim.x);
-    const int total = H * ctx;
-    const __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
-    const __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
-    int f = (blockIdx.x * MG_CONSUMERS + lane) * Lw;
-    const int f1 = min(f + Lw, total);
-    while (f < f1) {
-        const int h = f / ctx;
-        const int t0 = f - h * ctx;
-        const int t1 = min(ctx, t0 + (f1 - f));
-        f += t1 - t0;
-        const int te = min(t1, pos);
-        if (te > t0) {
-            const size_t off = ((size_t)(h / rep) * P.max_ctx + t0) * D;
-            l2_prefetch(kc_l + off, (uint32_t)(te - t0) * D * 2);
-            l2_prefetch(vc_l + off, (uint32_t)(te - t0) * D * 2);
-        }
     }
 }
 
@@ -794,10 +532,9 @@ __device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, 
 }
 
 // ------------------------------------------------------------------ attention phase
-template <int D, bool LL>
+template <int D>
 __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, uint32_t& cnt, int warp,
-                                                int lane, unsigned in_flag = 0u, unsigned out_flag = 0u) {
-    constexpr bool ll = LL;
+                                                int lane) {
     constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2, D4 = D + 4;
     constexpr int ROWB = D * 2, CTM = (MG_SLOT_BYTES / ROWB) & ~7, NPASS = CTM / 8;   // tokens / 8-token passes per ring item
     const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
@@ -836,50 +573,12 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
             const __nv_bfloat16* qh = qkv + (size_t)h * D;
             const __nv_bfloat16* kh = qkv + (size_t)(H + hk) * D;
             float q1[(half + 31) / 32], q2[(half + 31) / 32], k1[(half + 31) / 32], k2[(half + 31) / 32];
-            if (ll) {
-                // q / k of this head as {2 x bf16, phase id} packets written by the qkv phase: all loads first, then re-poll
-                // whatever is not there yet (the poll replaces the grid barrier AND the load that followed it)
-                constexpr int NU = (half + 31) / 32;
-                const int eq = h * D, ek = (H + hk) * D;
-                if (lane < 3) {                                     // sentinels: last packet of this head's q, k and v rows
-                    const int e = (lane == 0 ? eq : lane == 1 ? ek : (H + KVH + hk) * D) + D - 2;
-                    PollGuard g;
-                    uint2 r = ld_poll2(P.qkv_ll + (e >> 1));
-                    while (r.y != in_flag) { g.spin("qkv sentinel", in_flag, r.y); r = ld_poll2(P.qkv_ll + (e >> 1)); }
-                }
-                __syncwarp();
-                uint2 pq1[NU], pq2[NU], pk1[NU], pk2[NU];
 #pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    const int j = lane + u * 32;
-                    if (j < half) {
-                        pq1[u] = ld_poll2(P.qkv_ll + ((eq + j) >> 1)); pq2[u] = ld_poll2(P.qkv_ll + ((eq + j + half) >> 1));
-                        pk1[u] = ld_poll2(P.qkv_ll + ((ek + j) >> 1)); pk2[u] = ld_poll2(P.qkv_ll + ((ek + j + half) >> 1));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    const int j = lane + u * 32;
-                    if (j < half) {
-                        PollGuard g;
-                        while (pq1[u].y != in_flag || pq2[u].y != in_flag || pk1[u].y != in_flag || pk2[u].y != in_flag) {
-                            g.spin("qkv", in_flag, pq1[u].y);
-                            pq1[u] = ld_poll2(P.qkv_ll + ((eq + j) >> 1)); pq2[u] = ld_poll2(P.qkv_ll + ((eq + j + half) >> 1));
-                            pk1[u] = ld_poll2(P.qkv_ll + ((ek + j) >> 1)); pk2[u] = ld_poll2(P.qkv_ll + ((ek + j + half) >> 1));
-                        }
-                        auto pick = [](uint2 pkt, int e) { return __uint_as_float((e & 1) ? (pkt.x & 0xffff0000u) : (pkt.x << 16)); };
-                        q1[u] = pick(pq1[u], eq + j); q2[u] = pick(pq2[u], eq + j + half);
-                        k1[u] = pick(pk1[u], ek + j); k2[u] = pick(pk2[u], ek + j + half);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < (half + 31) / 32; ++u) {
-                    const int j = lane + u * 32;
-                    if (j < half) {
-                        q1[u] = __bfloat162float(__ldcg(qh + j)); q2[u] = __bfloat162float(__ldcg(qh + j + half));
-                        k1[u] = __bfloat162float(__ldcg(kh + j)); k2[u] = __bfloat162float(__ldcg(kh + j + half));
-                    }
+            for (int u = 0; u < (half + 31) / 32; ++u) {
+                const int j = lane + u * 32;
+                if (j < half) {
+                    q1[u] = __bfloat162float(__ldcg(qh + j)); q2[u] = __bfloat162float(__ldcg(qh + j + half));
+                    k1[u] = __bfloat162float(__ldcg(kh + j)); k2[u] = __bfloat162float(__ldcg(kh + j + half));
                 }
             }
 #pragma unroll
@@ -900,21 +599,10 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
         const int tend = has_new ? pos : t1;
         const __nv_bfloat16* vnew = qkv + (size_t)(H + KVH + hk) * D;
         uint4 vn[VPL];                                  // this lane's slice of the new v row
-        // 8 consecutive elements of the new v row from packets (element index e0, multiple of 8): two 16-byte loads, four flags
-        auto v8_ll = [&](int e0) -> uint4 {
-            const uint2* src = P.qkv_ll + (e0 >> 1);
-            PollGuard g;
-            uint4 a = ld_poll4(src), b = ld_poll4(src + 2);
-            while (a.y != in_flag || a.w != in_flag || b.y != in_flag || b.w != in_flag) {
-                g.spin("v", in_flag, a.y);
-                a = ld_poll4(src); b = ld_poll4(src + 2);
-            }
-            return make_uint4(a.x, a.z, b.x, b.z);
-        };
         if (has_new) {
 #pragma unroll
             for (int i = 0; i < VPL; ++i)
-                vn[i] = ll ? v8_ll((H + KVH + hk) * D + sub * EPL + i * 8) : ldcg4(vnew + sub * EPL + i * 8);
+                vn[i] = ldcg4(vnew + sub * EPL + i * 8);
             if ((h % rep) == 0 && lane < D / 8) {
                 // exactly one segment per kv head appends the new row to the cache (for FUTURE steps; this step uses the
                 // locally rotated copy, so there is no intra-phase dependency on this write)
@@ -923,9 +611,7 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                 kq.x = pack_bf16(s8[0], s8[1]); kq.y = pack_bf16(s8[2], s8[3]);
                 kq.z = pack_bf16(s8[4], s8[5]); kq.w = pack_bf16(s8[6], s8[7]);
                 *reinterpret_cast<uint4*>(kc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = kq;
-                *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) =
-                    ll ? v8_ll((H + KVH + hk) * D + lane * 8) : ldcg4(vnew + lane * 8);
-                __threadfence();                   // flags-in-data mode: ordered before this warp's partial packets (no barrier follows)
+                *reinterpret_cast<uint4*>(vc_l + ((size_t)hk * P.max_ctx + pos) * D + lane * 8) = ldcg4(vnew + lane * 8);
                 fence_proxy_async_global();        // later steps read this row with bulk copies (async proxy)
             }
         }
@@ -1084,17 +770,6 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                 }
             }
             const int c0 = (hh * ctx) / Lc;
-            if (ll) {
-                if constexpr (D <= 96) {
-                    uint4* pk = P.att_ll + ((size_t)hh * P.att_maxp + (c - c0)) * 33;
-                    float n1 = 0.f, n2 = 0.f;
-                    if constexpr (D > 32) n1 = num[1];
-                    if constexpr (D > 64) n2 = num[2];
-                    st_packet4(pk + lane, num[0], n1, n2, out_flag);       // dims lane, lane + 32, lane + 64
-                    if (lane == 0) st_packet4(pk + 32, M, L, 0.f, out_flag);
-                }
-                continue;
-            }
             float* dst = P.att_ws + ((size_t)hh * P.att_maxp + (c - c0)) * D4;
 #pragma unroll
             for (int i = 0; i < (D + 31) / 32; ++i) {
@@ -1108,15 +783,15 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
 #undef ATR
 }
 
-template <int D, bool LL>
+template <int D>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* tokens_out, float* logits_out,
-                   long long eos_id, long long pad_id, unsigned flag_base) {
+                   long long eos_id, long long pad_id) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[MG_CONSUMERS * MG_SLOTS], s_empty[MG_CONSUMERS * MG_SLOTS];
     __shared__ float s_red[MG_CONSUMERS];
     __shared__ float s_rope[2 * 128];
-    __shared__ unsigned s_epoch, s_prod_ord;
+    __shared__ unsigned s_epoch;
     const MegaPlan& P = *plan_g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Smem S;
@@ -1130,7 +805,6 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
 
     if (tid == 0) {
         s_epoch = 0;
-        s_prod_ord = 0;
         for (int s = 0; s < MG_CONSUMERS * MG_SLOTS; ++s) {
             ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
@@ -1143,50 +817,28 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
     if (warp == MG_CONSUMERS) {
         // ------------------------------------------------------------ producer: every step's weights, in order
         uint32_t pc = 0;
-        const int inflight = P.inflight, inflight_cur = P.inflight_cur;
         const int ppos0 = P.st->ctx_len;
         const unsigned bps = 5u * P.n_layers + 2u;     // grid barriers per step (consumer side)
-        unsigned ord = 0;
         for (int stp = 0; stp < n_steps; ++stp)
             for (int i = 0; i < n_ops; ++i) {
                 const MegaOp op = P.ops[i];
                 // consumer epoch (grid barriers passed) while they work on this phase: 5 phases per layer, qkv first
                 const int l = i >> 2, j = i & 3;
                 const unsigned my_epoch = (unsigned)stp * bps + 5u * l + (j == 0 ? 0u : j + 1u);
-                produce_phase(op, S, pc, inflight, inflight_cur, &s_epoch, my_epoch, lane, &s_prod_ord, ord);
-                ord += (unsigned)cta_items(op);
-                if (j == 0 && i + 1 < n_ops && !(P.ablate & 2)) {          // after qkv: this layer's K / V stream
+                produce_phase(op, S, pc, MG_INFLIGHT_AHEAD, MG_INFLIGHT_CUR, &s_epoch, my_epoch, lane);
+                if (j == 0 && i + 1 < n_ops) {                              // after qkv: this layer's K / V stream
                     const unsigned need = stp > 0 ? (unsigned)(stp - 1) * bps + 5u * l + 2u : 0u;
-                    produce_attention<D>(P, l, ppos0 + stp, S, pc, inflight, inflight_cur, my_epoch + 1u, lane, &s_epoch, need);
+                    produce_attention<D>(P, l, ppos0 + stp, S, pc, MG_INFLIGHT_AHEAD, MG_INFLIGHT_CUR, my_epoch + 1u, lane, &s_epoch, need);
                 }
-            }
-        if (lane == 0) s_prod_ord = ord;
-        return;
-    }
-    if (warp == MG_CONSUMERS + 1) {
-        // ------------------------------------------------------------ L2 prefetcher: same item order, `pf_win` items ahead
-        const int win = P.pf_win;
-        if (win <= 0) return;
-        const int ppos0 = P.st->ctx_len;
-        unsigned ord = 0;
-        for (int stp = 0; stp < n_steps; ++stp)
-            for (int i = 0; i < n_ops; ++i) {
-                const MegaOp op = P.ops[i];
-                prefetch_phase(op, &s_prod_ord, ord, win, lane);
-                ord += (unsigned)cta_items(op);
-                if ((i & 3) == 0 && i + 1 < n_ops && !(P.ablate & 2))
-                    prefetch_attention<D>(P, i >> 2, ppos0 + stp, &s_prod_ord, ord, win, lane);
             }
         return;
     }
     // ---------------------------------------------------------------- consumers
-    unsigned epoch = 0, bars = 0;
-    constexpr bool ll = LL;
+    unsigned epoch = 0;
     uint32_t cnt = 0;
     const int pos0 = P.st->ctx_len;                     // position == cache slot of the first token processed
     const int step0 = P.st->step;
     const bool tracing = P.trace != nullptr;
-    const int ablate = P.ablate;                        // bring-up timing ablations (GVL_MEGA_ABLATE), 0 in production
     if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 2] = (long long)globaltimer_ns();
     for (int stp = 0; stp < n_steps; ++stp) {
         const int pos = pos0 + stp, step = step0 + stp;
@@ -1202,64 +854,45 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         MegaOp op = P.ops[0];
         NormPre np;
         prefetch_norm(op, np, tid);
-        // phase ids of this step (flags-in-data mode): flag_base + step * bps + phase + 1, phase = 5 l + {qkv, attn, o, gate_up, down}
-        const unsigned pid0 = flag_base + (unsigned)stp * (5u * P.n_layers + 2u) + 1u;
-        auto boundary = [&]() {
-            if (ll && !(ablate & 16)) phase_end(epoch, tid, &s_epoch);      // ablate 16: packets AND grid barriers (isolates the data path)
-            else grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate);
-        };
+        auto boundary = [&]() { grid_barrier(P.grid_bar, epoch, tid, &s_epoch); };
         for (int l = 0; l < P.n_layers; ++l) {
-            const unsigned pq = pid0 + 5u * l;          // id of this layer's qkv phase
+            long long* occ = (tracing && l == P.n_layers - 1) ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
             // norm + qkv
-            if (!(ablate & 4)) {
-                if (ll && !(op.from_embed & 1)) stage_x_ll(op, pq - 1u, S, tid, warp, lane);           // x from down(l-1)
-                else stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
-            }
+            stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
             tr.mark(tid);
-            long long* occ = tracing ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
-            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ : nullptr, pq);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ);
             op = P.ops[l * 4 + 1];
             tr.mark(tid); boundary(); tr.mark(tid);
             // rope + KV append + split-KV attention
-            if (!(ablate & 2)) attention_phase<D, LL>(P, l, pos, S, cnt, warp, lane, pq, pq + 1u);
+            attention_phase<D>(P, l, pos, S, cnt, warp, lane);
             tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
             tr.mark(tid); boundary(); tr.mark(tid);
             // merge + o_proj + residual
-            if (!(ablate & 4)) {
-                if (ll) stage_x_attn_ll(P, pq + 1u, S, pos + 1, tid);
-                else stage_x_attn(P, S, pos + 1, tid);
-            }
+            stage_x_attn(P, S, pos + 1, tid);
             tr.mark(tid);
-            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 8 : nullptr, pq + 2u);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 8 : nullptr);
             op = P.ops[l * 4 + 2];
-            if (!ll) prefetch_norm(op, np, tid);
+            prefetch_norm(op, np, tid);
             tr.mark(tid); boundary(); tr.mark(tid);
             // norm + gate_up + SwiGLU
-            if (!(ablate & 4)) {
-                if (ll) stage_x_ll(op, pq + 2u, S, tid, warp, lane);
-                else stage_x_vec(op, op.x, np, S, tid, warp, lane);
-            }
+            stage_x_vec(op, op.x, np, S, tid, warp, lane);
             tr.mark(tid);
-            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 16 : nullptr, pq + 3u);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 16 : nullptr);
             op = P.ops[l * 4 + 3];
             tr.mark(tid); boundary(); tr.mark(tid);
             // down + residual
-            if (!(ablate & 4)) {
-                if (ll) stage_x_ll(op, pq + 3u, S, tid, warp, lane);
-                else stage_x_vec(op, op.x, np, S, tid, warp, lane);
-            }
+            stage_x_vec(op, op.x, np, S, tid, warp, lane);
             tr.mark(tid);
-            gemv_items<LL>(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, (occ && l == P.n_layers - 1) ? occ + 24 : nullptr, pq + 4u);
+            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 24 : nullptr);
             op = P.ops[l * 4 + 4];
-            if (!ll) prefetch_norm(op, np, tid);
+            prefetch_norm(op, np, tid);
             tr.mark(tid); boundary(); tr.mark(tid);
         }
         // norm + lm_head + bias + greedy pick
-        if (ll) stage_x_ll(op, pid0 + 5u * P.n_layers - 1u, S, tid, warp, lane);
-        else stage_x_vec(op, op.x, np, S, tid, warp, lane);
+        stage_x_vec(op, op.x, np, S, tid, warp, lane);
         tr.mark(tid);
-        gemv_items<LL>(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
-        tr.mark(tid); grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate); tr.mark(tid);
+        gemv_items(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
+        tr.mark(tid); boundary(); tr.mark(tid);
         // ---- bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
         if (blockIdx.x == 0 && tid == 0) {
             DecodeState* st = P.st;
@@ -1274,7 +907,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             st->attn_len = pos + 1;
             st->step = step + 1;
         }
-        if (stp + 1 < n_steps) grid_barrier(P.grid_bar, epoch, bars, tid, &s_epoch, ablate);   // the next step reads cur_token
+        if (stp + 1 < n_steps) boundary();              // the next step reads cur_token
     }
     if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 1] = (long long)globaltimer_ns();
 }
@@ -1345,57 +978,32 @@ bool decode_mega_finalize(MegaPlan* p) {
     int xb = maxk * 2;
     if (att_scratch_bytes(D) > xb) xb = att_scratch_bytes(D);
     p->x_bytes = (xb + 127) & ~127;
-    p->part_items = items;
+    {
+        // partial-sum buffer: the largest phase in one pass if it fits; otherwise what is left of shared memory (gemv_items then runs
+        // that phase in passes). At least 64 items (8 units of 8 segments) must fit.
+        const long avail = (long)MG_SMEM_LIMIT - MG_RING_BYTES - p->x_bytes;
+        long cap = avail / 32;
+        if (cap < 64) return false;
+        p->part_items = items < cap ? items : (int)cap;
+    }
     p->att_maxp = G / H + 2;
-    const char* ab = getenv("GVL_MEGA_ABLATE");
-    p->ablate = ab ? atoi(ab) : 0;
-    const char* env = getenv("GVL_MEGA_INFLIGHT");
-    p->inflight = env ? atoi(env) : 1;
-    const char* ec = getenv("GVL_MEGA_INFLIGHT_CUR");
-    p->inflight_cur = ec ? atoi(ec) : MG_SLOTS;
-    const char* pw = getenv("GVL_MEGA_PFWIN");
-    p->pf_win = pw ? atoi(pw) : 0;                     // measured slower with the prefetcher on (profiles/r1_decode.md)
-    if (p->inflight < 1) p->inflight = 1;
-    if (p->inflight > MG_SLOTS) p->inflight = MG_SLOTS;
-    if (p->inflight_cur < p->inflight) p->inflight_cur = p->inflight;
-    if (p->inflight_cur > MG_SLOTS) p->inflight_cur = MG_SLOTS;
-    return (size_t)MG_RING_BYTES + p->x_bytes + (size_t)items * 32 <= (size_t)MG_SMEM_LIMIT;
+    return (size_t)MG_RING_BYTES + p->x_bytes + (size_t)p->part_items * 32 <= (size_t)MG_SMEM_LIMIT;
 }
 
 size_t decode_mega_att_ws_bytes(const MegaPlan* p) {
     return (size_t)p->heads * p->att_maxp * (p->head_dim + 4) * sizeof(float);
 }
 
-unsigned decode_mega_phase_ids(const MegaPlan* p, int n_steps) { return (unsigned)n_steps * (5u * p->n_layers + 2u); }
-
-// Flags-in-data mode needs every CTA in every phase's dependency chain (that is what bounds the skew between CTAs to one phase
-// and makes the in-place reuse of the x / qkv / mid / partial buffers safe without grid barriers): every GEMV op of a layer must
-// have at least gridDim units, outputs in whole packets; the partial packets hold 3 floats per lane -> head_dim <= 96, and the
-// merge keeps <= 8 partials per head in registers.
-bool decode_mega_ll_supported(const MegaPlan* p) {
-    const int G = num_sms();
-    if (p->head_dim > 96 || p->att_maxp > 8) return false;
-    for (int i = 0; i < p->n_layers * 4; ++i) {
-        const MegaOp& op = p->ops[i];
-        if (op.units < G || op.n_out % 8 != 0 || op.K % 4 != 0 || op.K > 8192) return false;
-    }
-    return p->ops[p->n_layers * 4].K <= 8192;
-}
-
-size_t decode_mega_att_ll_packets(const MegaPlan* p) { return (size_t)p->heads * p->att_maxp * 33; }
-
 int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
-                       long long eos_id, long long pad_id, unsigned flag_base, cudaStream_t s) {
+                       long long eos_id, long long pad_id, cudaStream_t s) {
     const size_t smem = (size_t)MG_RING_BYTES + hp->x_bytes + (size_t)hp->part_items * 32;
-    using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long, unsigned);
+    using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long);
     const int di = hp->head_dim == 64 ? 0 : hp->head_dim == 96 ? 1 : 2;
-    KernelT kern = hp->use_ll ? (di == 0 ? decode_mega_kernel<64, true> : decode_mega_kernel<96, true>)
-                              : (di == 0 ? decode_mega_kernel<64, false> : di == 1 ? decode_mega_kernel<96, false>
-                                                                                 : decode_mega_kernel<128, false>);
-    static size_t attr_set_tab[64][2][3] = {};         // per device (cudaFuncSetAttribute is per device), per kernel variant
+    KernelT kern = di == 0 ? decode_mega_kernel<64> : di == 1 ? decode_mega_kernel<96> : decode_mega_kernel<128>;
+    static size_t attr_set_tab[64][3] = {};            // per device (cudaFuncSetAttribute is per device), per kernel variant
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t* attr_set = attr_set_tab[dev & 63][hp->use_ll ? 1 : 0];
+    size_t* attr_set = attr_set_tab[dev & 63];
     if (attr_set[di] < smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return GVL_ERR_CUDA;
@@ -1412,7 +1020,7 @@ int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, plan_dev, n_steps, tokens_out, logits_out, eos_id, pad_id, flag_base) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, kern, plan_dev, n_steps, tokens_out, logits_out, eos_id, pad_id) != cudaSuccess)
         return GVL_ERR_CUDA;
     g_launch_count++;
     return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;

@@ -26,10 +26,6 @@ struct MegaOp {                 // one weight-streaming GEMV phase (M = 1)
     const __nv_bfloat16* bias;
     const __nv_bfloat16* residual;
     void* out;
-    // flags-in-data hand-off (MegaPlan::use_ll): the same vectors as {2 x bf16, 32-bit phase id} packets
-    const uint2* x_ll;
-    const uint2* res_ll;
-    uint2* out_ll;
 };
 
 constexpr int MEGA_MAX_LAYERS = 48;
@@ -40,10 +36,6 @@ constexpr int MEGA_TRACE_ATT_OFF = 960;  // + 8 warps x 8 marks inside the atten
 
 struct MegaPlan {
     int n_layers, dim, heads, kv_heads, head_dim, vocab, max_ctx;
-    int ablate;                 // bring-up only (GVL_MEGA_ABLATE): 1 skip grid barriers, 2 skip attention, 4 skip staging, 8 skip the GEMV math
-    int inflight;               // bulk copies each producer lane keeps outstanding (1..3; GVL_MEGA_INFLIGHT)
-    int inflight_cur;           // ... once the consumers have reached the phase being produced (GVL_MEGA_INFLIGHT_CUR)
-    int pf_win;                 // L2 prefetch distance ahead of the ring producer, in 8 KB items per CTA (0 = off; GVL_MEGA_PFWIN)
     int x_bytes;                // activation staging area (also the attention-phase scratch)
     int part_items;             // capacity of the per-item partial-sum buffer (8 floats per item)
     int att_maxp;               // split-KV partials per head in att_ws
@@ -58,12 +50,6 @@ struct MegaPlan {
     unsigned long long* amax;   // packed (orderable logit, ~index) of the greedy pick; zero between steps
     unsigned* grid_bar;
     DecodeState* st;
-    // Flags-in-data phase hand-off (GVL_MEGA_LL=1; Phi-like shapes: head_dim <= 96, every GEMV phase has >= gridDim units): the
-    // x / qkv / mid vectors travel as 8-byte {2 x bf16, phase id} packets and the split-KV partials as 16-byte {3 floats, phase id}
-    // packets, so a phase polls the data it needs instead of a grid barrier followed by a second round trip for the data.
-    int use_ll;
-    uint2 *x_ll, *qkv_ll, *mid_ll;
-    uint4* att_ll;              // [heads][att_maxp][33]: packet l < 32 = dims (l, l+32, l+64), packet 32 = (m, l, -)
     long long* trace;           // optional [gridDim.x][MEGA_TRACE_STRIDE] phase timestamps of the LAST step (bring-up / profiling)
 };
 
@@ -72,14 +58,10 @@ bool decode_mega_shape(MegaOp* op);
 // packed copy of one weight matrix (elements; device-side repack of W [n_rows, ldw])
 size_t decode_mega_packed_elems(const MegaOp* op);
 int decode_mega_pack(const MegaOp* op, const __nv_bfloat16* W, int ldw, __nv_bfloat16* dst, cudaStream_t s);
-// after all ops are set: picks x_bytes / part_items / att_maxp / inflight; false when the step does not fit
+// after all ops are set: picks x_bytes / part_items / att_maxp; false when the step does not fit
 bool decode_mega_finalize(MegaPlan* plan);
 size_t decode_mega_att_ws_bytes(const MegaPlan* plan);
-// flag_base: phase ids of this launch are flag_base + 1 ...; the caller advances it by decode_mega_phase_ids(plan, n_steps)
 int decode_mega_launch(const MegaPlan* plan_host, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
-                       long long eos_id, long long pad_id, unsigned flag_base, cudaStream_t s);
-unsigned decode_mega_phase_ids(const MegaPlan* plan, int n_steps);
-bool decode_mega_ll_supported(const MegaPlan* plan);       // after decode_mega_finalize
-size_t decode_mega_att_ll_packets(const MegaPlan* plan);
+                       long long eos_id, long long pad_id, cudaStream_t s);
 
 }  // namespace gvl

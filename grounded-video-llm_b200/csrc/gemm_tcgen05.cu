@@ -379,12 +379,10 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo
         BN = (waste256 * 8 > N || tiles256 < num_sms()) ? 128 : 256;
         if (act == ACT_SWIGLU) BN = 256;
     }
-    // 2-CTA (cta_group::2) 256x256 tiles when the problem fills the 74 CTA pairs; GVL_GEMM_2CTA=0/1 forces it.
+    // 2-CTA (cta_group::2) 256x256 tiles when the problem fills the 74 CTA pairs (bn_hint = 128 keeps the 1-CTA kernel: tests, A/B)
     {
-        static const char* env = getenv("GVL_GEMM_2CTA");
         const long tiles2 = long((M + 255) / 256) * ((N + 255) / 256);
-        const bool want = env ? (env[0] == '1') : true;
-        if (want && BN == 256 && bn_hint != 128 && tiles2 >= num_sms() / 2) {
+        if (BN == 256 && bn_hint != 128 && tiles2 >= num_sms() / 2) {
             prof_begin(GVL_PROF_GEMM, 2.0 * M * (double)N * K, stream);
             int rc2 = gemm_bf16_2cta(A, lda, W, ldw, out, ldo, M, N, K, bias, gamma, residual, ldr, act, res, out_f32, stream);
             prof_end(GVL_PROF_GEMM, stream);

@@ -215,13 +215,6 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
               const __nv_bfloat16* residual, int ldr, int act, int out_f32, cudaStream_t s) {
     if (M < 1 || M > GV_MAXM || K % 256 != 0 || (act != 0 && act != 3)) return GVL_ERR_ARG;
     if (act == 3 && N % 256 != 0) return GVL_ERR_ARG;
-    {
-        // GVL_GEMV_BULK=1 selects the shared-memory-staged cp.async.bulk kernel (gemv_bulk.cu); it measured SLOWER
-        // than this file's register-staged kernel in round 1 (profiles/r1_decode.md) and is kept for A/B work only.
-        static const char* env = getenv("GVL_GEMV_BULK");
-        if (env && env[0] == '1')
-            return gemv_bulk_bf16(x, ldx, W, ldw, out, ldo, M, N, K, norm_w, eps, bias, residual, ldr, act, out_f32, s);
-    }
     const size_t smem = (size_t)M * K * 2;
     prof_begin(GVL_PROF_GEMV, 2.0 * (double)N * K, s);  // algorithmic bytes: the weight matrix, read once
     const int units = act == 3 ? N / 2 : (N + 1) / 2;
@@ -231,11 +224,13 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
 #define GV_LAUNCH(MT, SW)                                                                                             \
     do {                                                                                                              \
         auto kern = gemv3_kernel<MT, SW>;                                                                             \
-        static size_t max_set = 0;                                                                                    \
-        if (smem > 48 * 1024 && smem > max_set) {                                                                     \
+        static size_t max_set[64] = {};                        /* per device: cudaFuncSetAttribute is per device */          \
+        int dev_ = 0;                                                                                                 \
+        cudaGetDevice(&dev_);                                                                                         \
+        if (smem > 48 * 1024 && smem > max_set[dev_ & 63]) {                                                          \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)   \
                 return GVL_ERR_CUDA;                                                                                  \
-            max_set = smem;                                                                                           \
+            max_set[dev_ & 63] = smem;                                                                                \
         }                                                                                                             \
         if (launch_k(kern, dim3(grid), dim3(GV_THREADS), smem, s, x, ldx, W, ldw, out, ldo, N, K, norm_w, eps, bias,    \
                      residual, ldr, out_f32) != cudaSuccess) return GVL_ERR_CUDA;                                       \

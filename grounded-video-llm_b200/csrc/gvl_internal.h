@@ -98,7 +98,6 @@ int attention_mma_fwd(const AttnArgs& a, cudaStream_t stream);    // attention.c
 bool attention_tc_supported(const AttnArgs& a);                   // attention_tc.cu (tcgen05/TMEM/TMA, d in 64/96/128)
 int attention_tc_fwd(const AttnArgs& a, cudaStream_t stream);
 int attention_tc2_fwd(const AttnArgs& a, cudaStream_t stream);    // attention_tc2.cu (two query tiles per CTA)
-int attention_tc3_fwd(const AttnArgs& a, cudaStream_t stream);    // attention_tc3.cu (+ double-buffered 64-key score tiles)
 
 // rowops.cu
 int layernorm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows,

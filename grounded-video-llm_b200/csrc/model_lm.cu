@@ -50,9 +50,6 @@ struct gvl_lm {
     float* mega_att_ws = nullptr;
     __nv_bfloat16* mega_w = nullptr;  // packed decode copy of every layer's weights + lm_head (decode_mega_pack)
     unsigned long long* amax = nullptr;
-    uint2 *ll_x = nullptr, *ll_qkv = nullptr, *ll_mid = nullptr;   // flags-in-data vectors of the single-kernel step (GVL_MEGA_LL)
-    uint4* ll_att = nullptr;
-    unsigned ll_epoch = 0;            // phase ids handed out so far (unique across launches)
     long long* trace = nullptr;       // GVL_MEGA_TRACE=1: per-CTA phase timestamps of the last decode step
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
@@ -129,11 +126,7 @@ int enqueue_decode_step_impl(gvl_lm* lm, long long* tokens_out, float* logits_ou
 int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, long long eos_id, long long pad_id,
                         cudaStream_t s) {
     if (lm->use_mega && lm->plan_dev)
-    {
-        const unsigned base = lm->ll_epoch;
-        lm->ll_epoch += decode_mega_phase_ids(lm->plan_host, 1);
-        return decode_mega_launch(lm->plan_host, lm->plan_dev, 1, tokens_out, logits_out, eos_id, pad_id, base, s);
-    }
+        return decode_mega_launch(lm->plan_host, lm->plan_dev, 1, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = lm->use_pdl;
     const int rc = enqueue_decode_step_impl(lm, tokens_out, logits_out, eos_id, pad_id, s);
     g_pdl = false;
@@ -236,35 +229,6 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
                 aok = aok && dev_alloc(&lm->grid_bar, 1) == GVL_OK && dev_alloc(&lm->plan_dev, 1) == GVL_OK &&
                            dev_alloc(&lm->amax, 1) == GVL_OK &&
                            dev_alloc(&lm->mega_att_ws, decode_mega_att_ws_bytes(hp) / sizeof(float)) == GVL_OK;
-                {
-                    // flags-in-data phase hand-off: opt-in (GVL_MEGA_LL=1). Parity-green at full width, but measured SLOWER than the
-                    // grid-barrier hand-off in round 1 (3.1-3.6 vs 2.5 ms/step, profiles/r1_decode.md), so barriers stay the default
-                    const char* le = getenv("GVL_MEGA_LL");
-                    hp->use_ll = 0;
-                    if (aok && (le && le[0] == '1') && decode_mega_ll_supported(hp)) {
-                        const size_t nx = (size_t)w->dim / 2, nq = (size_t)qkv_n / 2, nm = (size_t)w->ffn / 2;
-                        const size_t na = decode_mega_att_ll_packets(hp);
-                        aok = dev_alloc(&lm->ll_x, nx) == GVL_OK && dev_alloc(&lm->ll_qkv, nq) == GVL_OK &&
-                              dev_alloc(&lm->ll_mid, nm) == GVL_OK && dev_alloc(&lm->ll_att, na) == GVL_OK &&
-                              cudaMemset(lm->ll_x, 0, nx * sizeof(uint2)) == cudaSuccess &&
-                              cudaMemset(lm->ll_qkv, 0, nq * sizeof(uint2)) == cudaSuccess &&
-                              cudaMemset(lm->ll_mid, 0, nm * sizeof(uint2)) == cudaSuccess &&
-                              cudaMemset(lm->ll_att, 0, na * sizeof(uint4)) == cudaSuccess;
-                        if (aok) {
-                            hp->use_ll = 1;
-                            hp->x_ll = lm->ll_x; hp->qkv_ll = lm->ll_qkv; hp->mid_ll = lm->ll_mid; hp->att_ll = lm->ll_att;
-                            for (int l = 0; l < w->n_layers; ++l) {
-                                MegaOp* o = &hp->ops[l * 4];
-                                o[0].x_ll = lm->ll_x;   o[0].out_ll = lm->ll_qkv; o[0].res_ll = nullptr;
-                                o[1].x_ll = nullptr;    o[1].out_ll = lm->ll_x;   o[1].res_ll = lm->ll_x;
-                                o[2].x_ll = lm->ll_x;   o[2].out_ll = lm->ll_mid; o[2].res_ll = nullptr;
-                                o[3].x_ll = lm->ll_mid; o[3].out_ll = lm->ll_x;   o[3].res_ll = lm->ll_x;
-                            }
-                            MegaOp* h = &hp->ops[w->n_layers * 4];
-                            h->x_ll = lm->ll_x; h->out_ll = nullptr; h->res_ll = nullptr;
-                        }
-                    }
-                }
                 if (aok) {
                     hp->grid_bar = lm->grid_bar;
                     hp->amax = lm->amax;
@@ -293,7 +257,6 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
     cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar); cudaFree(lm->trace);
     cudaFree(lm->mega_att_ws); cudaFree(lm->amax); cudaFree(lm->mega_w);
-    cudaFree(lm->ll_x); cudaFree(lm->ll_qkv); cudaFree(lm->ll_mid); cudaFree(lm->ll_att);
     delete lm->plan_host;
     if (lm->cs) cudaStreamDestroy(lm->cs);
     if (lm->ev_in) cudaEventDestroy(lm->ev_in);
@@ -376,9 +339,7 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
     CU(cudaMemcpyAsync(&lm->st->step, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
     if (lm->use_mega && lm->plan_dev) {
         // one cooperative launch runs all the steps (token / position / EOS state stay in device memory)
-        const unsigned base = lm->ll_epoch;
-        lm->ll_epoch += decode_mega_phase_ids(lm->plan_host, n_steps);
-        CK(decode_mega_launch(lm->plan_host, lm->plan_dev, n_steps, lm->tok_buf, lbuf, eos_id, pad_id, base, s));
+        CK(decode_mega_launch(lm->plan_host, lm->plan_dev, n_steps, lm->tok_buf, lbuf, eos_id, pad_id, s));
     } else if (!lm->use_graph) {
         for (int i = 0; i < n_steps; ++i) CK(enqueue_decode_step(lm, lm->tok_buf, lbuf, eos_id, pad_id, s));
     } else {
@@ -430,6 +391,8 @@ int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas
     if (stride) *stride = MEGA_TRACE_STRIDE;
     return GVL_OK;
 }
+
+int gvl_lm_decode_kind(const gvl_lm* lm) { return (lm && lm->use_mega && lm->plan_dev) ? 1 : 0; }
 
 const long long* gvl_lm_first_token(gvl_lm* lm) { return lm ? lm->first_tok : nullptr; }
 

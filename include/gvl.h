@@ -232,6 +232,10 @@ int gvl_profile_collect(int kind, double* total_ms, double* total_work, long lon
  * host (synchronises the device). Returns GVL_ERR_STATE when tracing is off.                                          */
 int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas, int* stride);
 
+/* which decode step this object runs: 1 = the single persistent kernel (decode_mega.cu), 0 = the per-op chain (CUDA graph).
+ * The single kernel is the default whenever the shape fits it; GVL_DECODE_MEGA=0 in the environment at create time selects the chain. */
+int gvl_lm_decode_kind(const gvl_lm* lm);
+
 /* first generated token (argmax of the prefill logits), device int64 */
 const long long* gvl_lm_first_token(gvl_lm* lm);
 /* Sampling decode (HF generate with do_sample=True, llava_next_video.py:655-661 / inference.py:170-176): the caller picks the

@@ -41,10 +41,12 @@ class RefCpuSampler:
         self.threads = threads or os.cpu_count() or 1
         torch.set_num_threads(self.threads)
         rope = synth.phi35_rope(96)
-        with torch.no_grad():
+        with torch.no_grad(), RM.no_init():
             self.clip = RM.build_clip(device="cpu").float()
             self.iv2 = RM.build_iv2(frames=8, depth=3, flash=False, device="cpu", dtype=torch.float32)
             self.lm = {n: RM.build_lm("phi3", RM.phi3_config(layers=n, rope=rope), device="cpu", dtype=torch.float32) for n in (1, 2)}
+        for i, m in enumerate([self.clip, self.iv2] + list(self.lm.values())):
+            RM.fast_fill_(m, seed=i, threads=self.threads)
         g = torch.Generator().manual_seed(1234)
         self.img = torch.randn(1, 3, 336, 336, generator=g)
         self.seg = torch.randn(1, 3, 8, 224, 224, generator=g)
@@ -86,11 +88,23 @@ def cfg1_end_to_end(threads=None, new_tokens=16, seed=0):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
-    params, lm_cfg, _, _ = synth.make_params("phi3.5", device="cpu", seed=seed, lm_dtype=torch.float32)
-    ref = RM.build_vlm(params, "phi3.5", lm_cfg, frames_per_seg=8, device="cpu", flash=False)
+    # random-init modules of the named architecture, built directly in fp32 (the reference's CPU dtype); parameters drawn with the
+    # parallel filler instead of the modules' single-threaded initialisers
+    small = dict(lm=dict(synth.PHI35, layers=1, vocab=8), clip=dict(synth.CLIP_L336, layers=1), iv2=dict(synth.IV2_1B, depth=1))
+    params, lm_cfg, _, _ = synth.make_params("phi3.5", device="cpu", seed=seed, lm_dtype=torch.float32, **small)
+    with RM.no_init():
+        vt = RM.build_clip(device="cpu").float()
+        ve = RM.build_iv2(frames=8, depth=40, flash=False, device="cpu", dtype=torch.float32)
+        lm = RM.build_lm("phi3", RM.phi3_config(rope=lm_cfg["rope"]), device="cpu", dtype=torch.float32)
+        f = RM.build_vlm(params, "phi3.5", lm_cfg, frames_per_seg=8, device="cpu", flash=False, with_lm=False,
+                         clip_kw=dict(layers=1), iv2_kw=dict(depth=1))          # projectors, glb_GN / sub_GN, bound methods
+    for i, m in enumerate((vt, ve, lm)):
+        RM.fast_fill_(m, seed=seed * 10 + i, threads=threads)
+    f.vision_tower, f.video_encoder, f.language_model = vt, ve, lm
+    f.multi_modal_projector, f.video_projecter = f.multi_modal_projector.float(), f.video_projecter.float()
+    f.dtype = torch.float32
+    f.config = type("C", (), {"hidden_size": 3072})()
     del params
-    f = ref.float_copy()
-    del ref
     t_build = time.perf_counter() - t0
     s = synth.make_clip_inputs(1, num_frames=8, num_segs=1)
     ids = torch.tensor(s["input_ids"][0])[None]

@@ -24,6 +24,70 @@ def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
 
 
+@contextlib.contextmanager
+def no_init():
+    """Construct reference modules WITHOUT running their random initialisers (single-threaded RNG: ~2 minutes for the fp32 3.8B
+    decoder on the host): torch.nn.init.* and the modules' reset_parameters / _init_weights become no-ops for the duration;
+    the caller fills the parameters with fast_fill_() afterwards. Timing infrastructure only (oracle/ref_bench.py)."""
+    import torch.nn.init as I
+    mods = R.import_models()
+    saved = []
+
+    def patch(obj, name, fn):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, fn)
+
+    ident = lambda t, *a, **k: t
+    for name in ("trunc_normal_", "normal_", "uniform_", "xavier_uniform_", "xavier_normal_", "kaiming_uniform_", "kaiming_normal_",
+                 "constant_", "zeros_", "ones_"):
+        patch(I, name, ident)
+    for cls in (nn.Linear, nn.Embedding, nn.Conv2d, nn.Conv3d, nn.LayerNorm):
+        patch(cls, "reset_parameters", lambda self: None)
+    for key, cname in (("phi3", "Phi3PreTrainedModel"), ("llama", "LlamaPreTrainedModel"), ("clip", "CLIPPreTrainedModel")):
+        patch(getattr(mods[key], cname), "_init_weights", lambda self, module: None)
+    iv = mods["iv2"]
+    patch(iv.PretrainInternVideo2, "_init_weights", lambda self, m: None)
+    patch(iv.PretrainInternVideo2, "fix_init_weight", lambda self: None)
+    patch(iv, "trunc_normal_", ident)
+    try:
+        yield
+    finally:
+        for obj, name, old in reversed(saved):
+            setattr(obj, name, old)
+
+
+def fast_fill_(module, seed=0, std=0.02, threads=None):
+    """Seeded normal(0, std) for every matrix / embedding / conv weight, drawn in parallel chunks (one generator per chunk; torch
+    releases the GIL), ones for norm weights, zeros for biases and the rest, 1e-5 for LayerScale gammas (as constructed)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    threads = threads or os.cpu_count() or 1
+    jobs = []
+    for n, (name, p) in enumerate(module.named_parameters()):
+        d = p.data
+        if d.dim() >= 2 and "pos" not in name and "cls" not in name:
+            flat = d.view(-1)
+            step = max(1 << 22, (flat.numel() + threads - 1) // threads)
+            for c, i in enumerate(range(0, flat.numel(), step)):
+                jobs.append((flat[i:i + step], seed * 1000003 + n * 1009 + c))
+        elif name.endswith("gamma"):
+            d.fill_(1e-5)
+        elif name.endswith("weight") and d.dim() == 1:
+            d.fill_(1.0)
+        elif d.dim() >= 2:
+            jobs.append((d.view(-1), seed * 1000003 + n * 1009))
+        else:
+            d.zero_()
+
+    def work(job):
+        t, sd = job
+        t.normal_(0.0, std, generator=torch.Generator().manual_seed(sd))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, jobs))
+    return module
+
+
 def flash_attn_usable(device="cuda"):
     """True if the installed flash_attn wheel runs on this device (2.8.3 may lack sm_100 kernels)."""
     try:

@@ -303,25 +303,36 @@ def test_lm_decode_single_kernel_ring_fed_kv(gvl, arch, heads, kvh, hd, ctx, mon
     lm2.close()
 
 
-def test_lm_decode_flags_in_data_full_width(gvl, monkeypatch):
-    """Phi-3.5 width (dim 3072, 32 x 96 heads, ffn 8192): the shape where the single-kernel step hands its phases over with
-    flags-in-data packets instead of grid barriers (GVL_MEGA_LL=1, opt-in). Same logits as the barrier mode and the per-op
-    chain up to accumulation-order noise, oracle parity, and repeated generate calls (phase ids keep counting across launches,
-    one-step launches of the sampling path included)."""
+def test_lm_decode_full_width_repeatable_and_tracing(gvl, monkeypatch):
+    """Phi-3.5 width (dim 3072, 32 x 96 heads, ffn 8192), 2 layers: the single-kernel step and the per-op chain against the oracle,
+    bit-identical results across repeated generate calls and step granularities (the sampling path launches one step at a time),
+    and the GVL_MEGA_TRACE profiling switch (per-CTA phase timestamps through gvl_lm_mega_trace) leaves the results untouched."""
     dev = "cuda"
     P = O.make_lm_params(arch="phi3", dim=3072, heads=32, kv_heads=32, head_dim=96, ffn=8192, layers=2, vocab=1000, seed=17, std=0.02)
     rope = O.phi35_rope_cfg(96)
     cfg = dict(arch="phi3", layers=2, heads=32, kv_heads=32, head_dim=96, eps=1e-5, rope=rope)
     emb = torch.randn(700, 3072, generator=torch.Generator().manual_seed(6)) * 0.05
     outs = {}
-    for name, env in (("ll", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_LL": "1"}), ("bar", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_LL": "0"}),
-                      ("chain", {"GVL_DECODE_MEGA": "0"})):
+    for name, env in (("traced", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_TRACE": "1"}), ("bar", {"GVL_DECODE_MEGA": "1", "GVL_MEGA_TRACE": ""}),
+                      ("chain", {"GVL_DECODE_MEGA": "0", "GVL_MEGA_TRACE": ""})):
         for k, v in env.items():
-            monkeypatch.setenv(k, v)
+            if v:
+                monkeypatch.setenv(k, v)
+            else:
+                monkeypatch.delenv(k, raising=False)
         lm = gvl.model.CausalLM(P, "phi3", 32, 32, 96, 1e-5, rope, max_ctx=1024)
         runs = [lm.generate(inputs_embeds=emb.to(dev)[None], max_new_tokens=6, return_logits=True) for _ in range(3)]
         samp = lm.generate(inputs_embeds=emb.to(dev)[None], max_new_tokens=6, do_sample=True, top_k=1, return_logits=True)
         outs[name] = runs + [samp]
+        if name == "traced":
+            import ctypes
+            from gvl import _lib
+            buf = np.zeros((160, 1024), dtype=np.int64)
+            n, st = ctypes.c_int(), ctypes.c_int()
+            rc = _lib.load().gvl_lm_mega_trace(lm._active[0], buf.ctypes.data_as(ctypes.c_void_p), 160, ctypes.byref(n), ctypes.byref(st))
+            assert rc == 0 and n.value > 0 and st.value == 1024
+            marks = buf[: n.value, 3:3 + 2 * 15]                       # 2 layers x 5 phases x 3 marks per CTA: monotone clock64
+            assert (np.diff(marks, axis=1) > 0).all()
         lm.close()
     toks_ref, lg_ref = O.greedy_decode(emb.to(dev), {k: v.to(dev) for k, v in P.items()}, cfg, 6, mode="bf16")
     tol = _logit_tol(lg_ref)
@@ -335,10 +346,8 @@ def test_lm_decode_flags_in_data_full_width(gvl, monkeypatch):
             same += 1
         assert same >= 2, name
         _cmp(l0[0][: same + 1], lg_ref[: same + 1], atol=tol)
-    same = 0
-    while same < 5 and int(outs["ll"][0][0][0, same]) == int(outs["bar"][0][0][0, same]):
-        same += 1
-    _cmp(outs["ll"][0][1][0][: same + 1], outs["bar"][0][1][0][: same + 1], atol=tol)
+    assert outs["traced"][0][0].tolist() == outs["bar"][0][0].tolist()
+    _cmp(outs["traced"][0][1][0], outs["bar"][0][1][0], atol=1e-6)
 
 
 @pytest.mark.parametrize("mega", ["1", "0"])
@@ -553,3 +562,35 @@ def test_generate_cap_chunks_and_abi_bounds(gvl):
     assert 0 <= int(scratch[0]) < 1000
     lm.close()
     lm2.close()
+
+
+def test_lm_decode_llama_width_runs_in_the_single_kernel(gvl, monkeypatch):
+    """Llama-3-8B widths (dim 4096, 32 q / 8 kv heads x 128, ffn 14336, vocab 128558), 1 layer: with x staging at 28 KB the
+    per-item partial sums of the gate_up and lm_head phases no longer fit shared memory at once, so those phases run in PASSES
+    (decode_mega.cu gemv_items). Round 1 fell back to the per-op chain for this shape. Single kernel vs chain vs oracle."""
+    dev = "cuda"
+    P = {k: v.to(dev) for k, v in O.make_lm_params(arch="llama", dim=4096, heads=32, kv_heads=8, head_dim=128, ffn=14336, layers=1,
+                                                   vocab=128558, seed=31, std=0.02).items()}
+    rope = dict(type="plain", base=500000.0, bf16_quirk=True)
+    cfg = dict(arch="llama", layers=1, heads=32, kv_heads=8, head_dim=128, eps=1e-5, rope=rope)
+    emb = (torch.randn(300, 4096, generator=torch.Generator().manual_seed(32)) * 0.05).to(dev)
+    from gvl import _lib
+    outs = {}
+    for name, mega in (("mega", "1"), ("chain", "0")):
+        monkeypatch.setenv("GVL_DECODE_MEGA", mega)
+        lm = gvl.model.CausalLM(P, "llama", 32, 8, 128, 1e-5, rope, max_ctx=512)
+        outs[name] = lm.generate(inputs_embeds=emb[None], max_new_tokens=4, return_logits=True)
+        assert _lib.load().gvl_lm_decode_kind(lm._active[0]) == (1 if mega == "1" else 0)
+        lm.close()
+    toks_ref, lg_ref = O.greedy_decode(emb, P, cfg, 4, mode="bf16")
+    tol = _logit_tol(lg_ref)
+    for name, (t, l) in outs.items():
+        assert t[0].tolist() == l[0].argmax(-1).tolist(), name
+        same = 0
+        while same < 3 and int(t[0, same]) == int(toks_ref[same]):
+            same += 1
+        _cmp(l[0][: same + 1], lg_ref[: same + 1], atol=tol)
+    same = 0
+    while same < 3 and int(outs["mega"][0][0, same]) == int(outs["chain"][0][0, same]):
+        same += 1
+    _cmp(outs["mega"][1][0][: same + 1], outs["chain"][1][0][: same + 1], atol=tol)

@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "grounded-video-llm_b200"))
-from gvl import hostlogic, model, synth  # noqa: E402
+from gvl import _lib, hostlogic, model, synth  # noqa: E402
 
 
 def main():
@@ -60,7 +60,8 @@ def main():
     print(json.dumps({"config": "BASELINE configs[3]: Llama-3-8B, 96 frames, S=%d, %d decode tokens, 1 GPU" % (S, a.decode),
                       "videos_per_s": 1e3 / total, "ms_per_video": total, "encode_images_ms": enc, "splice+prefill_ms": pre,
                       "decode_ms_per_token": dec_ms, "decode_gbs": byts / dec_ms / 1e6, "decode_frac_of_hbm_peak": byts / dec_ms / 1e6 / peak,
-                      "decode_kernel": "per-op chain" if os.environ.get("GVL_DECODE_MEGA", "1") == "0" else "decode_mega_kernel<128>"}))
+                      "decode_kernel": "decode_mega_kernel<128> (single persistent kernel)" if _lib.load().gvl_lm_decode_kind(m.language_model._active[0])
+                                       else "per-op chain (gemv3_kernel + decode_attn_kernel, CUDA graph)"}))
 
 
 if __name__ == "__main__":
