@@ -181,7 +181,9 @@ def run_gvl_arm(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout; rank 0 must print exactly ONE JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+        import datetime
+        # a collective that one rank never enters must fail in minutes, not hold the box for the default 10-minute watchdog
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev), timeout=datetime.timedelta(seconds=180))
     lib = _lib.load()
     B = world * args.clips_per_gpu
     params, lm_cfg, clip_cfg, iv2_cfg = synth.make_params("phi3.5", device=dev, seed=0)
@@ -366,8 +368,8 @@ def run_gvl_arm(args):
         for _ in range(2):
             m.generate(one, max_new_tokens=DECODE_TOKENS)
         strong_ms = timed(one, False, 3) / 3
+        t1 = m.generate(one, max_new_tokens=DECODE_TOKENS)[0]          # every rank: generate issues collectives
         if rank == 0:
-            t1 = m.generate(one, max_new_tokens=DECODE_TOKENS)[0]
             assert hashlib.sha256(",".join(str(int(x)) for x in t1.tolist()).encode()).hexdigest()[:16] == tok_sha, \
                 "clip 0 decoded from units encoded on %d ranks differs from the weak-scaling run" % world
     if rank == 0:

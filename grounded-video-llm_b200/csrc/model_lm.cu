@@ -51,6 +51,16 @@ struct gvl_lm {
     __nv_bfloat16* mega_w = nullptr;  // packed decode copy of every layer's weights + lm_head (decode_mega_pack)
     unsigned long long* amax = nullptr;
     long long* trace = nullptr;       // GVL_MEGA_TRACE=1: per-CTA phase timestamps of the last decode step
+    // batched decode (gvl_lm_decode_batch): activation rows of up to GVL_LM_MAX_BATCH sequences side by side, owned by the FIRST object
+    // of a batch; one CUDA graph per batch composition
+    __nv_bfloat16 *bx = nullptr, *bqkv = nullptr, *bq = nullptr, *battn = nullptr, *bmid = nullptr;
+    float* blogits = nullptr;
+    cudaGraphExec_t bgraph = nullptr;
+    gvl_lm* b_members[4] = {nullptr, nullptr, nullptr, nullptr};
+    int b_n = 0;
+    bool b_logits = false;
+    long long b_eos = 0, b_pad = 0;
+    unsigned b_warm_mask = 0;         // batch sizes whose kernels have run once outside capture (function attributes set)
 
     size_t kv_layer_elems() const { return (size_t)2 * w.kv_heads * w.max_ctx * w.head_dim; }
     __nv_bfloat16* kcache(int l) const { return kv + (size_t)l * kv_layer_elems(); }
@@ -137,7 +147,9 @@ int enqueue_decode_step(gvl_lm* lm, long long* tokens_out, float* logits_out, lo
 
 extern "C" {
 
-int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
+int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) { return gvl_lm_create_ex(w, 0, out); }
+
+int gvl_lm_create_ex(const gvl_lm_weights* w, int flags, gvl_lm** out) {
     if (!w || !out || w->n_layers <= 0 || !w->layers) return GVL_ERR_ARG;
     if (w->dim % 256 != 0 || w->ffn % 256 != 0 || (w->heads * w->head_dim) % 256 != 0) return GVL_ERR_ARG;
     if (w->head_dim != 64 && w->head_dim != 96 && w->head_dim != 128) return GVL_ERR_ARG;
@@ -166,7 +178,7 @@ int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out) {
     {
         const char* env = getenv("GVL_DECODE_MEGA");
         // single-kernel decode step is the default (measured faster than the per-op chain); GVL_DECODE_MEGA=0 selects the chain
-        lm->use_mega = !(env && env[0] == '0') && w->n_layers <= MEGA_MAX_LAYERS;
+        lm->use_mega = !(env && env[0] == '0') && !(flags & GVL_LM_NO_SINGLE_KERNEL) && w->n_layers <= MEGA_MAX_LAYERS;
         if (lm->use_mega) {
             MegaPlan* hp = new MegaPlan();
             memset(hp, 0, sizeof(MegaPlan));
@@ -257,6 +269,8 @@ void gvl_lm_destroy(gvl_lm* lm) {
     cudaFree(lm->dlogits); cudaFree(lm->da_ws); cudaFree(lm->st); cudaFree(lm->first_tok);
     cudaFree(lm->tok_buf); cudaFree(lm->logit_buf); cudaFree(lm->plan_dev); cudaFree(lm->grid_bar); cudaFree(lm->trace);
     cudaFree(lm->mega_att_ws); cudaFree(lm->amax); cudaFree(lm->mega_w);
+    if (lm->bgraph) cudaGraphExecDestroy(lm->bgraph);
+    cudaFree(lm->bx); cudaFree(lm->bqkv); cudaFree(lm->bq); cudaFree(lm->battn); cudaFree(lm->bmid); cudaFree(lm->blogits);
     delete lm->plan_host;
     if (lm->cs) cudaStreamDestroy(lm->cs);
     if (lm->ev_in) cudaEventDestroy(lm->ev_in);
@@ -379,6 +393,139 @@ int gvl_lm_decode(gvl_lm* lm, int n_steps, long long* tokens_out, float* logits_
     CU(cudaEventRecord(lm->ev_out, s));
     CU(cudaStreamWaitEvent(caller, lm->ev_out, 0));
     lm->host_ctx += n_steps;
+    return GVL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Batched greedy decode: n_seq <= 4 sequences that were prefilled on their OWN gvl_lm objects (own KV cache, own decode state, own RoPE
+// table) over the SAME weights advance together. Every weight matrix is streamed once per step for all sequences (gemv3_kernel with
+// M = n_seq activation rows: the weights are 7.4 of the 8.8 GB a Phi-3.5 step moves); RoPE + KV append, the q_len = 1 attention and the
+// greedy pick stay per sequence. Semantics per sequence are those of gvl_lm_decode (HF greedy: EOS -> pad afterwards).
+// Reference: the batched `language_model.generate` of llava_next_video.py:655-661 (rows are independent; positions per row).
+static int enqueue_batch_step(gvl_lm* const* lms, int n, long long eos_id, long long pad_id, bool want_logits, cudaStream_t s) {
+    gvl_lm* L0 = lms[0];
+    const gvl_lm_weights& w = L0->w;
+    const int D = w.dim, H = w.heads, KVH = w.kv_heads, hd = w.head_dim, F = w.ffn;
+    const int HD = H * hd, qkv_n = (H + 2 * KVH) * hd;
+    const float scale = 1.0f / sqrtf((float)hd);
+    for (int b = 0; b < n; ++b) {
+        CK(step_begin(lms[b]->st, s));
+        CK(embed_token((const __nv_bfloat16*)w.embed, lms[b]->st, L0->bx + (size_t)b * D, D, w.vocab, s));
+    }
+    for (int l = 0; l < w.n_layers; ++l) {
+        const gvl_lm_layer& L = L0->layers[l];
+        CK(gemv_bf16(L0->bx, D, (const __nv_bfloat16*)L.qkv_w, D, L0->bqkv, qkv_n, n, qkv_n, D, (const __nv_bfloat16*)L.in_norm_w,
+                     w.rms_eps, nullptr, nullptr, 0, 0, 0, s));
+        for (int b = 0; b < n; ++b) {
+            gvl_lm* m = lms[b];
+            CK(rope_decode(L0->bqkv + (size_t)b * qkv_n, L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l),
+                           (const __nv_bfloat16*)m->w.rope_cos, (const __nv_bfloat16*)m->w.rope_sin, m->st, H, KVH, hd, m->w.max_ctx, s));
+            CK(decode_attention(L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l), L0->battn + (size_t)b * HD, m->da_ws,
+                                &m->st->attn_len, H, KVH, hd, m->w.max_ctx, scale, s));
+        }
+        CK(gemv_bf16(L0->battn, HD, (const __nv_bfloat16*)L.o_w, HD, L0->bx, D, n, D, HD, nullptr, 0.f, nullptr, L0->bx, D, 0, 0, s));
+        CK(gemv_bf16(L0->bx, D, (const __nv_bfloat16*)L.gate_up_w, D, L0->bmid, F, n, 2 * F, D, (const __nv_bfloat16*)L.post_norm_w,
+                     w.rms_eps, nullptr, nullptr, 0, 3, 0, s));
+        CK(gemv_bf16(L0->bmid, F, (const __nv_bfloat16*)L.down_w, F, L0->bx, D, n, D, F, nullptr, 0.f, nullptr, L0->bx, D, 0, 0, s));
+    }
+    CK(gemv_bf16(L0->bx, D, (const __nv_bfloat16*)w.lm_head_w, D, L0->blogits, w.vocab, n, w.vocab, D, (const __nv_bfloat16*)w.final_norm_w,
+                 w.rms_eps, (const __nv_bfloat16*)w.lm_head_b, nullptr, 0, 0, 1, s));
+    for (int b = 0; b < n; ++b)
+        CK(step_end(L0->blogits + (size_t)b * w.vocab, w.vocab, lms[b]->st, lms[b]->tok_buf, want_logits ? lms[b]->logit_buf : nullptr,
+                    eos_id, pad_id, s));
+    return GVL_OK;
+}
+
+int gvl_lm_decode_batch(gvl_lm* const* lms, int n_seq, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
+                        long long pad_id, void* stream) {
+    if (!lms || n_seq < 1 || n_seq > 4 || n_steps < 0) return GVL_ERR_ARG;
+    gvl_lm* L0 = lms[0];
+    if (!L0) return GVL_ERR_ARG;
+    for (int b = 0; b < n_seq; ++b) {
+        gvl_lm* m = lms[b];
+        if (!m) return GVL_ERR_ARG;
+        for (int c = 0; c < b; ++c)
+            if (lms[c] == m) return GVL_ERR_ARG;                                   // one object = one sequence
+        // same weights (the objects differ in KV cache, decode state, RoPE table and max_ctx only)
+        if (m->w.n_layers != L0->w.n_layers || m->w.dim != L0->w.dim || m->w.vocab != L0->w.vocab || m->w.embed != L0->w.embed ||
+            m->w.lm_head_w != L0->w.lm_head_w || m->layers[0].qkv_w != L0->layers[0].qkv_w) return GVL_ERR_ARG;
+        if (m->host_ctx < 0 || m->host_ctx + n_steps > m->w.max_ctx) return GVL_ERR_STATE;
+    }
+    if (n_steps == 0) return GVL_OK;
+    cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+    cudaStream_t s = L0->cs;
+    const gvl_lm_weights& w = L0->w;
+    const int qkv_n = (w.heads + 2 * w.kv_heads) * w.head_dim;
+    if (!L0->bx) {
+        CK(dev_alloc(&L0->bx, (size_t)4 * w.dim));
+        CK(dev_alloc(&L0->bqkv, (size_t)4 * qkv_n));
+        CK(dev_alloc(&L0->bq, (size_t)4 * w.heads * w.head_dim));
+        CK(dev_alloc(&L0->battn, (size_t)4 * w.heads * w.head_dim));
+        CK(dev_alloc(&L0->bmid, (size_t)4 * w.ffn));
+        CK(dev_alloc(&L0->blogits, (size_t)4 * w.vocab));
+    }
+    CU(cudaEventRecord(L0->ev_in, caller));
+    CU(cudaStreamWaitEvent(s, L0->ev_in, 0));
+    const bool want_logits = logits_out != nullptr;
+    bool regraph = L0->bgraph == nullptr || L0->b_n != n_seq || L0->b_logits != want_logits || L0->b_eos != eos_id || L0->b_pad != pad_id;
+    int zero = 0;
+    for (int b = 0; b < n_seq; ++b) {
+        gvl_lm* m = lms[b];
+        if (L0->b_members[b] != m) regraph = true;
+        if (want_logits && m->logit_steps < n_steps) {
+            cudaFree(m->logit_buf);
+            m->logit_buf = nullptr;
+            CK(dev_alloc(&m->logit_buf, (size_t)n_steps * w.vocab));
+            m->logit_steps = n_steps;
+            if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }      // the single-sequence graph bound the old buffer
+            regraph = true;
+        }
+        CU(cudaMemcpyAsync(&m->st->step, &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    if (regraph) {
+        if (L0->bgraph) { cudaGraphExecDestroy(L0->bgraph); L0->bgraph = nullptr; }
+        if (!(L0->b_warm_mask & (1u << n_seq))) {
+            // one eager step outside capture (cudaFuncSetAttribute must not be issued while capturing); undone by restoring the states
+            DecodeState saved[4];
+            for (int b = 0; b < n_seq; ++b) CU(cudaMemcpyAsync(&saved[b], lms[b]->st, sizeof(DecodeState), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            g_pdl = L0->use_pdl;
+            int rc0 = enqueue_batch_step(lms, n_seq, -1, 0, false, s);
+            g_pdl = false;
+            if (rc0 != GVL_OK) return rc0;
+            for (int b = 0; b < n_seq; ++b) CU(cudaMemcpyAsync(lms[b]->st, &saved[b], sizeof(DecodeState), cudaMemcpyHostToDevice, s));
+            CU(cudaStreamSynchronize(s));
+            L0->b_warm_mask |= 1u << n_seq;
+        }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const long long launches_before = g_launch_count;
+        g_pdl = L0->use_pdl;
+        int rc = enqueue_batch_step(lms, n_seq, eos_id, pad_id, want_logits, s);
+        g_pdl = false;
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        g_launch_count = launches_before;
+        if (rc != GVL_OK || e != cudaSuccess) { if (g) cudaGraphDestroy(g); return rc != GVL_OK ? rc : GVL_ERR_CUDA; }
+        e = cudaGraphInstantiate(&L0->bgraph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return GVL_ERR_CUDA;
+        L0->b_n = n_seq; L0->b_logits = want_logits; L0->b_eos = eos_id; L0->b_pad = pad_id;
+        for (int b = 0; b < 4; ++b) L0->b_members[b] = b < n_seq ? lms[b] : nullptr;
+    }
+    const long long per_step = 2LL * n_seq + (long long)w.n_layers * (4 + 2 * n_seq) + 1 + n_seq;
+    for (int i = 0; i < n_steps; ++i) {
+        CU(cudaGraphLaunch(L0->bgraph, s));
+        g_launch_count += per_step;
+    }
+    for (int b = 0; b < n_seq; ++b) {
+        gvl_lm* m = lms[b];
+        if (tokens_out) CU(cudaMemcpyAsync(tokens_out + (size_t)b * n_steps, m->tok_buf, (size_t)n_steps * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+        if (want_logits) CU(cudaMemcpyAsync(logits_out + (size_t)b * n_steps * w.vocab, m->logit_buf, (size_t)n_steps * w.vocab * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, s));
+        m->host_ctx += n_steps;
+    }
+    CU(cudaEventRecord(L0->ev_out, s));
+    CU(cudaStreamWaitEvent(caller, L0->ev_out, 0));
     return GVL_OK;
 }
 

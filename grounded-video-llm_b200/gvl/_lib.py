@@ -99,11 +99,13 @@ _SIGS = {
     "gvl_iv2_workspace": (c_sz, [ctypes.POINTER(Iv2Weights), c_i]),
     "gvl_iv2_encode": (c_i, [ctypes.POINTER(Iv2Weights), c_vp, c_vp, c_i, c_vp, c_sz, c_vp]),
     "gvl_lm_create": (c_i, [ctypes.POINTER(LmWeights), ctypes.POINTER(c_vp)]),
+    "gvl_lm_create_ex": (c_i, [ctypes.POINTER(LmWeights), c_i, ctypes.POINTER(c_vp)]),
     "gvl_lm_destroy": (None, [c_vp]),
     "gvl_lm_prefill": (c_i, [c_vp, c_vp, c_i, c_vp, c_vp, c_vp]),
     "gvl_lm_decode": (c_i, [c_vp, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_first_token": (c_vp, [c_vp]),
     "gvl_lm_decode_kind": (c_i, [c_vp]),
+    "gvl_lm_decode_batch": (c_i, [ctypes.POINTER(c_vp), c_i, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_set_next_token": (c_i, [c_vp, c_vp, c_vp]),
     "gvl_lm_set_graph": (c_i, [c_vp, c_i]),
     "gvl_lm_mega_trace": (c_i, [c_vp, c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),

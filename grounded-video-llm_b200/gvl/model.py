@@ -138,12 +138,13 @@ class CausalLM:
                                              r["max_pos"], r["orig_max_pos"], False, long_from=long_from)
         return hostlogic.plain_rope_tables(self.max_ctx, hd, r["base"], bf16_matmul_quirk=r.get("bf16_quirk", False))
 
-    def _get(self, long_from):
+    def _get(self, long_from, slot=0):
         """One C-side LM object per RoPE table; the weight buffers are shared. LongRoPE (modeling_phi3.py:371-409) picks the
         factor set per forward call from kv_seq_len: `long_from` = first position rotated with long_factor -- 0 after a prompt
         longer than original_max_position_embeddings, original_max_position_embeddings otherwise (cached decode steps past it
         switch to long_factor while the keys already cached keep their rotation; hostlogic.longrope_tables)."""
-        if long_from not in self._lms:
+        key = long_from if slot == 0 else (long_from, slot)       # slot > 0: further sequences of a batch (own KV cache and state)
+        if key not in self._lms:
             lib = _lib.load()
             cos, sin = self._tables(long_from)
             h, kvh, hd, eps = self.cfg
@@ -158,10 +159,10 @@ class CausalLM:
                 pk.struct.rope_cos = ctypes.c_void_p(cos_d.data_ptr())
                 pk.struct.rope_sin = ctypes.c_void_p(sin_d.data_ptr())
             handle = ctypes.c_void_p()
-            rc = lib.gvl_lm_create(ctypes.byref(pk.struct), ctypes.byref(handle))
-            _lib.check(rc, "gvl_lm_create")
-            self._lms[long_from] = handle
-        return self._lms[long_from]
+            rc = lib.gvl_lm_create_ex(ctypes.byref(pk.struct), 0 if slot == 0 else 1, ctypes.byref(handle))   # 1 = GVL_LM_NO_SINGLE_KERNEL
+            _lib.check(rc, "gvl_lm_create_ex")
+            self._lms[key] = handle
+        return self._lms[key]
 
     @property
     def embed_table(self):
@@ -178,7 +179,7 @@ class CausalLM:
             return 0
         return 0 if prompt_len > r["orig_max_pos"] else r["orig_max_pos"]
 
-    def prefill(self, inputs_embeds, want_hidden=False, n_new=0):
+    def prefill(self, inputs_embeds, want_hidden=False, n_new=0, slot=0):
         """inputs_embeds [S,D] bf16. Returns (last-position fp32 logits [V], hidden [S,D] or None). `n_new` is only a
         capacity hint: generate() clamps the number of steps to the cache (max_new_tokens is a ceiling, not a reservation)."""
         lib = _lib.load()
@@ -186,7 +187,7 @@ class CausalLM:
         S = emb.shape[0]
         if S > self.max_ctx:
             raise ValueError("sequence of %d tokens exceeds max_ctx=%d" % (S, self.max_ctx))
-        lm = self._get(self._long_from(S))
+        lm = self._get(self._long_from(S), slot)
         logits = torch.empty((self.vocab,), dtype=torch.float32, device=self.device)
         hidden = torch.empty((S, self.dim), dtype=torch.bfloat16, device=self.device) if want_hidden else None
         rc = lib.gvl_lm_prefill(lm, ctypes.c_void_p(emb.data_ptr()), S, ctypes.c_void_p(logits.data_ptr()),
@@ -311,13 +312,69 @@ class CausalLM:
             lrows.append(r)
         return out, torch.stack(lrows, dim=0)
 
+    MAX_BATCH = 4             # sequences per gvl_lm_decode_batch call (GEMV kernel: up to 4 activation rows per weight pass)
+
+    def _greedy_group(self, embs, eos, pad_token_id, max_new_tokens, return_logits):
+        """Greedy decode of 2..4 unpadded sequences TOGETHER: each is prefilled on its own gvl_lm object (own KV cache), then all
+        advance in lock-step through gvl_lm_decode_batch, which streams every weight matrix once per step for the whole group.
+        Returns ([tokens_b], [logits_b or None])."""
+        lib = _lib.load()
+        nb = len(embs)
+        handles, firsts, first_logits, caps = [], [], [], []
+        for slot, emb in enumerate(embs):
+            fl, _ = self.prefill(emb, slot=slot)
+            lm, S = self._active
+            handles.append(lm)
+            caps.append(self._cap(S, max_new_tokens))
+            firsts.append(_wrap_device_i64(ctypes.c_void_p(lib.gvl_lm_first_token(lm)), self.device))
+            first_logits.append(fl)
+        n_cap = min(caps)
+        toks = torch.full((nb, n_cap), int(pad_token_id), dtype=torch.int64, device=self.device)
+        lg = torch.zeros((nb, n_cap, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+        for b in range(nb):
+            toks[b, 0:1].copy_(firsts[b])
+            if return_logits:
+                lg[b, 0].copy_(first_logits[b])
+        arr = (ctypes.c_void_p * nb)(*[h.value for h in handles])
+        done = 1
+        chunk = (n_cap - 1) if eos < 0 else self.EOS_CHECK_EVERY
+        finished = (toks[:, 0] == eos) if eos >= 0 else None
+        # a row whose FIRST token is EOS keeps stepping with the others (its later tokens are cut off below, like HF pads them)
+        while done < n_cap and not (finished is not None and bool(finished.all())):
+            n = min(chunk, n_cap - done)
+            tbuf = torch.empty((nb, n), dtype=torch.int64, device=self.device)
+            lbuf = torch.empty((nb, n, self.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            rc = lib.gvl_lm_decode_batch(arr, nb, n, ctypes.c_void_p(tbuf.data_ptr()),
+                                         ctypes.c_void_p(lbuf.data_ptr() if return_logits else 0), eos, int(pad_token_id), _stream())
+            _lib.check(rc, "gvl_lm_decode_batch")
+            toks[:, done:done + n] = tbuf
+            if return_logits:
+                lg[:, done:done + n] = lbuf
+            done += n
+            if eos >= 0:
+                finished = finished | (tbuf == eos).any(dim=1)
+        outs, logs = [], []
+        for b in range(nb):
+            t = toks[b, :done]
+            if eos >= 0:
+                hit = (t == eos).nonzero()
+                if hit.numel() > 0:
+                    first = int(hit[0])
+                    t = t.clone()
+                    t[first + 1:] = int(pad_token_id)
+            outs.append(t)
+            logs.append(lg[b, :done] if return_logits else None)
+        return outs, logs
+
     def generate(self, inputs_embeds=None, attention_mask=None, eos_token_id=None, pad_token_id=0, do_sample=False,
                  num_beams=1, max_new_tokens=16, temperature=None, top_p=None, top_k=50, generator=None, return_logits=False,
-                 **unused):
+                 batched=True, **unused):
         """generate for a batch of left-padded sequences (each row is compacted with its attention_mask and run
         as an unpadded sequence: identical to the reference's varlen path because padding carries mask 0 and
         position ids are mask-cumsum, modeling_phi3.py:1593-1599). Returns int64 [B, L] like HF generate from inputs_embeds
         (new tokens only): L = max_new_tokens when eos_token_id is None, else the step at which the last row hit EOS.
+        Greedy with more than one row: the rows are prefilled one by one on their own KV caches and then decoded TOGETHER in groups of
+        up to 4 (gvl_lm_decode_batch: one pass over the weights per step for the whole group; batched=False keeps them separate).
         do_sample=False: greedy, all steps of a chunk inside the library (one launch per EOS_CHECK_EVERY steps; one launch
         in total without EOS). do_sample=True: HF sampling (temperature, top_k -- HF's GenerationConfig default 50 --, top_p,
         multinomial), one library step per token. Decoding across Phi-3.5's LongRoPE switch (position 4096) follows the
@@ -333,10 +390,27 @@ class CausalLM:
         B = inputs_embeds.shape[0]
         outs, logs = [], []
         eos = -1 if eos_token_id is None else int(eos_token_id)
+        rows = []
         for b in range(B):
             emb = inputs_embeds[b]
             if attention_mask is not None:
                 emb = emb[attention_mask[b].to(emb.device).bool()]
+            rows.append(emb)
+        if B > 1 and batched:
+            # several clips on this GPU: decode them in groups that share every weight pass (decode is HBM-bound on the weights)
+            for g0 in range(0, B, self.MAX_BATCH):
+                grp = rows[g0:g0 + self.MAX_BATCH]
+                if len(grp) == 1:
+                    o, l = self.generate(inputs_embeds=grp[0][None], eos_token_id=eos_token_id, pad_token_id=pad_token_id,
+                                         max_new_tokens=max_new_tokens, return_logits=True, batched=False)
+                    o, l = [o[0]], [l[0] if return_logits else None]
+                else:
+                    o, l = self._greedy_group(grp, eos, pad_token_id, max_new_tokens, return_logits)
+                outs += o
+                logs += l
+            return self._stack_rows(outs, logs, eos_token_id, pad_token_id, return_logits)
+        for b in range(B):
+            emb = rows[b]
             first_logits, _ = self.prefill(emb)
             lm, S = self._active
             n_cap = self._cap(S, max_new_tokens)
@@ -543,9 +617,15 @@ class LLAVA_NEXT_VIDEO:
         if mine:
             sel = torch.tensor(mine, dtype=torch.long)
             embeds, _, masks = self.prepare_multimodal_inputs(ids[sel], None, mask[sel], feats, [video_ids[b] for b in mine])
+            # ONE call for the clips this rank owns: greedy rows are decoded together (CausalLM.generate, gvl_lm_decode_batch)
+            out = self.language_model.generate(inputs_embeds=embeds, attention_mask=masks, eos_token_id=eos_id, pad_token_id=pad_id, **gk)
             for i, b in enumerate(mine):
-                local[b] = self.language_model.generate(inputs_embeds=embeds[i:i + 1], attention_mask=masks[i:i + 1],
-                                                        eos_token_id=eos_id, pad_token_id=pad_id, **gk)[0]
+                row = out[i]
+                if eos_id is not None:
+                    hit = (row == int(eos_id)).nonzero()
+                    if hit.numel() > 0:
+                        row = row[: int(hit[0]) + 1]
+                local[b] = row
         rank, ws = gdist.world()
         if ws > 1:
             width = int(gk.get("max_new_tokens", 16))

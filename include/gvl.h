@@ -208,6 +208,10 @@ typedef struct gvl_lm gvl_lm;    /* opaque: KV cache, workspaces, decode CUDA gr
 /* Phi3ForCausalLM / LlamaForCausalLM forward + greedy generate (modeling_phi3.py:1249-1383, 1466-1551;
  * modeling_llama.py:934-1044, 1165-1256; HF GenerationMixin greedy loop, llava_next_video.py:655-661). */
 int gvl_lm_create(const gvl_lm_weights* w, gvl_lm** out);
+/* flags: GVL_LM_NO_SINGLE_KERNEL = do not build the packed weight copy of the single-kernel decode step (+7.4 GB for Phi-3.5) for this
+ * object -- for the additional per-sequence objects of a batch, which decode through gvl_lm_decode_batch.                              */
+#define GVL_LM_NO_SINGLE_KERNEL 1
+int gvl_lm_create_ex(const gvl_lm_weights* w, int flags, gvl_lm** out);
 void gvl_lm_destroy(gvl_lm* lm);
 /* prefill from inputs_embeds bf16 [S,D]; writes fp32 logits of the LAST position to logits_out[vocab]
  * (may be NULL), optionally all-position hidden states for tests via hidden_out bf16 [S,D] (may be NULL),
@@ -231,6 +235,13 @@ int gvl_profile_collect(int kind, double* total_ms, double* total_work, long lon
  * records clock64() per CTA at every phase boundary of the LAST step; this copies [n_ctas][stride] int64 marks to the
  * host (synchronises the device). Returns GVL_ERR_STATE when tracing is off.                                          */
 int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas, int* stride);
+
+/* Batched greedy decode: n_seq (1..4) sequences, each prefilled on its OWN gvl_lm object created over the SAME weight table (own KV
+ * cache / decode state / RoPE table), advance n_steps together; every weight matrix is streamed once per step for all of them.
+ * tokens_out: device int64 [n_seq][n_steps]; logits_out: optional device fp32 [n_seq][n_steps][vocab]. Per-sequence semantics are
+ * those of gvl_lm_decode (llava_next_video.py:655-661 with a batch of prompts). Runs the per-op kernel chain as one CUDA graph.  */
+int gvl_lm_decode_batch(gvl_lm* const* lms, int n_seq, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
+                        long long pad_id, void* stream);
 
 /* which decode step this object runs: 1 = the single persistent kernel (decode_mega.cu), 0 = the per-op chain (CUDA graph).
  * The single kernel is the default whenever the shape fits it; GVL_DECODE_MEGA=0 in the environment at create time selects the chain. */
