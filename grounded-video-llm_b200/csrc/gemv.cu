@@ -227,7 +227,7 @@ int gemv_bf16(const __nv_bfloat16* x, int ldx, const __nv_bfloat16* W, int ldw, 
         static size_t max_set[64] = {};                        /* per device: cudaFuncSetAttribute is per device */          \
         int dev_ = 0;                                                                                                 \
         cudaGetDevice(&dev_);                                                                                         \
-        if (smem > 48 * 1024 && smem > max_set[dev_ & 63]) {                                                          \
+        if (smem + 1024 > 48 * 1024 && smem > max_set[dev_ & 63]) {   /* + the kernel's static shared memory (M = 3, K = 8192 is 48 KB + 96 B) */                                                          \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)   \
                 return GVL_ERR_CUDA;                                                                                  \
             max_set[dev_ & 63] = smem;                                                                                \

@@ -637,3 +637,14 @@ def test_batched_greedy_decode_matches_single_sequence(gvl, arch):
         assert te[b, :min(cut, te.shape[1])].tolist() == row[:min(cut, te.shape[1])]
         assert all(t == 7 for t in te[b, cut:].tolist())
     lm.close()
+
+
+def test_gemv_three_rows_at_k_8192(gvl):
+    """M = 3 activation rows at K = 8192 stage exactly 48 KB of dynamic shared memory next to the kernel's static 96 bytes: the opt-in
+    attribute must be requested (a 3-clip batched decode of Phi-3.5's down projection failed to launch before)."""
+    g = torch.Generator().manual_seed(5)
+    x = O.bf(torch.randn(3, 8192, generator=g) * 0.5)
+    w = O.bf(torch.randn(512, 8192, generator=g) * 0.02)
+    out = gvl.ops.gemv(x.cuda().bfloat16(), w.cuda().bfloat16())
+    ref = O.bf(x @ w.t())
+    _cmp(out, ref, atol=0.03, rtol=0.02)
