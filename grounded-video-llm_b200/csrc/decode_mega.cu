@@ -332,12 +332,16 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
         upp = (P.part_items / ipu) / mult * mult;
     }
     unsigned long long key = 0ull;
+    long long wait_clk = 0;                                  // tracing only: cycles this warp spent waiting for ring items, items consumed
+    int n_waited = 0;
     for (int u0 = 0; u0 < nu; u0 += upp) {
         const int nu_p = min(upp, nu - u0);
         const int q_lo = u0 * ipu, q_hi = (u0 + nu_p) * ipu;
         for (int q = q_lo + warp; q < q_hi; q += MG_CONSUMERS) {
             const uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
+            const long long w0 = occ ? clock64() : 0;
             ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+            if (occ) { wait_clk += clock64() - w0; ++n_waited; }
             const int j = q / ipu, r = q - j * ipu;
             const int seg = r % nseg;
             uint32_t wa = ring_w + slot * MG_SLOT_BYTES;
@@ -405,6 +409,7 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
         }
         if (u0 + upp < nu) cbar();                       // the next pass overwrites the partial sums
     }
+    if (occ != nullptr && lane == 0) { occ[32 + warp] = wait_clk; occ[64 + warp] = n_waited; }
     if (op.argmax) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -1,0 +1,7 @@
+#!/bin/bash
+# round-2 validation: whole GPU suite, smoke, bench line
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2f_pytest.log 2>&1; tail -4 gpurun_out/r2f_pytest.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r2f_smoke.log 2>&1; tail -2 gpurun_out/r2f_smoke.log
+timeout 900 python bench.py > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r2f_bench.json
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --clips-per-gpu 4 > gpurun_out/r2f_bench_c4.json 2> gpurun_out/r2f_bench_c4.err; echo "c4 rc=$?"; cut -c1-260 gpurun_out/r2f_bench_c4.json

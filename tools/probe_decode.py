@@ -89,6 +89,10 @@ def main():
         occ = buf[: n.value, 768:800].reshape(n.value, 4, 8).astype(np.float64)
         print("  ring slots already landed when the phase starts (last layer, mean over CTAs x warps, of 3): "
               + ", ".join("%s %.2f" % (k, occ[:, i].mean()) for i, k in enumerate(["qkv", "o_proj", "gate_up", "down"])))
+        wt = buf[: n.value, 800:832].reshape(n.value, 4, 8).astype(np.float64)
+        ni = buf[: n.value, 832:864].reshape(n.value, 4, 8).astype(np.float64)
+        print("  last layer, per consumer warp: cycles spent WAITING for ring items / items consumed / phase work cycles (mean over CTAs x warps): "
+              + ", ".join("%s %.0f / %.1f" % (k, wt[:, i].mean(), ni[:, i].mean()) for i, k in enumerate(["qkv", "o_proj", "gate_up", "down"])))
         a = buf[: n.value, 960:1024].reshape(n.value, 8, 8).astype(np.float64)
         d = np.diff(a, axis=2)                                   # [cta, warp, 7]
         tot = a[:, :, 7] - a[:, :, 0]
