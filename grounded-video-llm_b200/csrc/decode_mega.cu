@@ -95,9 +95,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+// pairs of an 8-k group reordered for the B fragment of gemv_items: [P0 P1 P2 P3] -> [P0 P2 P1 P3]
+__device__ __forceinline__ uint4 x_perm(uint4 v) { return make_uint4(v.x, v.z, v.y, v.w); }
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -184,11 +191,12 @@ __device__ __forceinline__ float sumsq8(uint4 v) {
 
 // ------------------------------------------------------------------ x staging: vector in global memory (+ RMSNorm)
 __device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat16* xsrc, const NormPre& np, const Smem& S,
-                                            int tid, int warp, int lane) {
+                                            int tid, int warp, int lane, long long* sm = nullptr) {
+    if (sm != nullptr && tid == 0) sm[0] = clock64();
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
     const int kv = op.K / 8;
     if (op.norm_w == nullptr) {
-        for (int i = tid; i < kv; i += 256) reinterpret_cast<uint4*>(sx)[i] = ldcg4(xsrc + (size_t)i * 8);
+        for (int i = tid; i < kv; i += 256) reinterpret_cast<uint4*>(sx)[i] = x_perm(ldcg4(xsrc + (size_t)i * 8));
         cbar();
         return;
     }
@@ -205,15 +213,18 @@ __device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat1
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) S.red[warp] = ss;
+        if (sm != nullptr && tid == 0) sm[1] = clock64();
         cbar();
+        if (sm != nullptr && tid == 0) sm[2] = clock64();
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
         const float rstd = rsqrtf(t / op.K + op.eps);
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-            if (tid + u * 256 < kv) reinterpret_cast<uint4*>(sx)[tid + u * 256] = norm8(xv[u], np.v[u], rstd);
+            if (tid + u * 256 < kv) reinterpret_cast<uint4*>(sx)[tid + u * 256] = x_perm(norm8(xv[u], np.v[u], rstd));
         cbar();
+        if (sm != nullptr && tid == 0) sm[3] = clock64();
         return;
     }
     float ss = 0.f;
@@ -231,15 +242,76 @@ __device__ __forceinline__ void stage_x_vec(const MegaOp& op, const __nv_bfloat1
     for (int w = 0; w < MG_CONSUMERS; ++w) t += S.red[w];
     const float rstd = rsqrtf(t / op.K + op.eps);
     for (int i = tid; i < kv; i += 256)
-        reinterpret_cast<uint4*>(sx)[i] = norm8(reinterpret_cast<uint4*>(sx)[i], __ldg(reinterpret_cast<const uint4*>(op.norm_w) + i), rstd);
+        reinterpret_cast<uint4*>(sx)[i] = x_perm(norm8(reinterpret_cast<uint4*>(sx)[i], __ldg(reinterpret_cast<const uint4*>(op.norm_w) + i), rstd));
     cbar();
 }
 
 // ------------------------------------------------------------------ x staging: merge of the split-KV attention partials
-__device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid) {
+// Every CTA needs the whole merged vector, so every CTA reads all H x (<= G/H + 2) partial rows (~75 KB at H = 32) from L2 right
+// after a grid barrier, under the producer's HBM stream: what this step costs is L2 round trips, not bytes. The first version walked
+// a thread's D/32 element groups one after the other (3 dependent round trips for Phi-3.5, 7.9k cycles per layer in the trace). Fast
+// path (H <= 32, <= 6 partials per head): thread tid first issues the (max, sum) header of pair (head tid / 8, partial tid % 8) and
+// ALL partial rows of its D/32 element groups, then the softmax weights are exchanged through shared memory: one round trip.
+// Same arithmetic in the same order as the general path (bit-identical results).
+template <int D>
+__device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid, long long* sm = nullptr) {
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
-    const int D = P.head_dim, H = P.heads, D4 = D + 4, maxp = P.att_maxp;
+    const int H = P.heads, D4 = D + 4, maxp = P.att_maxp;
     const int Lc = att_warp_len(ctx, H, gridDim.x) * MG_CONSUMERS;
+    if (sm != nullptr && tid == 0) sm[0] = clock64();
+    constexpr int NS = 6, NG = D / 32;
+    if (maxp <= NS && H <= 32) {
+        float2* wl = reinterpret_cast<float2*>(S.part);          // [head][8] (softmax weight, partial sum) -- `part` is idle between GEMV phases
+        const int h1 = tid >> 3, s1 = tid & 7;
+        float2 hd1 = make_float2(-INFINITY, 0.f);
+        if (h1 < H) {
+            const int c0 = (h1 * ctx) / Lc, c1 = ((h1 + 1) * ctx - 1) / Lc;
+            if (s1 <= c1 - c0) hd1 = __ldcg(reinterpret_cast<const float2*>(P.att_ws + ((size_t)h1 * maxp + s1) * D4));
+        }
+        float4 ov[NG][NS];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const int e0 = (tid + i * 256) * 4, h = e0 / D, d0 = e0 - h * D;
+            const bool live = h < H;
+            int np = 0;
+            if (live) {
+                const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+                np = c1 - c0 + 1;
+            }
+            const float* base = P.att_ws + (size_t)h * maxp * D4 + 4 + d0;
+#pragma unroll
+            for (int s2 = 0; s2 < NS; ++s2)
+                ov[i][s2] = s2 < np ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)s2 * D4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float M = hd1.x;
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 1));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 4));
+        wl[tid] = make_float2(__expf(hd1.x - M), hd1.y);
+        if (sm != nullptr && tid == 0) sm[1] = clock64();
+        cbar();
+        if (sm != nullptr && tid == 0) sm[2] = clock64();
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const int e0 = (tid + i * 256) * 4, h = e0 / D;
+            if (h >= H) continue;
+            float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+            float den = 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < NS; ++s2) {
+                const float2 w = wl[h * 8 + s2];
+                den += w.x * w.y;
+                num.x += w.x * ov[i][s2].x; num.y += w.x * ov[i][s2].y; num.z += w.x * ov[i][s2].z; num.w += w.x * ov[i][s2].w;
+            }
+            const float inv = den > 0.f ? 1.0f / den : 0.f;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sx) + (e0 >> 3) * 4 + ((e0 >> 2) & 1);      // x_perm layout, see below
+            dst[0] = pack_bf16(num.x * inv, num.y * inv);
+            dst[2] = pack_bf16(num.z * inv, num.w * inv);
+        }
+        cbar();
+        if (sm != nullptr && tid == 0) sm[3] = clock64();
+        return;
+    }
     for (int gi = tid; gi < H * D / 4; gi += 256) {
         const int e0 = gi * 4, h = e0 / D, d0 = e0 - h * D;
         const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
@@ -282,10 +354,10 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
             }
         }
         const float inv = den > 0.f ? 1.0f / den : 0.f;
-        uint2 o;
-        o.x = pack_bf16(num.x * inv, num.y * inv);
-        o.y = pack_bf16(num.z * inv, num.w * inv);
-        *reinterpret_cast<uint2*>(sx + e0) = o;
+        // x_perm layout: elements e0..e0+3 are pairs (P0, P1) or (P2, P3) of their 8-k group -> words 0 / 2 or 1 / 3
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sx) + (e0 >> 3) * 4 + ((e0 >> 2) & 1);
+        dst[0] = pack_bf16(num.x * inv, num.y * inv);
+        dst[2] = pack_bf16(num.z * inv, num.w * inv);
     }
     cbar();
 }
@@ -301,7 +373,6 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     const int ipu = nsel * nseg;
     const int n_items = nu * ipu;
     const int g = lane >> 2, t = lane & 3;
-    const int nchunk2 = op.seg_len / 64;
     // residual of this thread's output column: loaded now, used in the epilogue (hides one L2 round trip)
     const __nv_bfloat16* res = (op.from_embed & 2) ? emb_row : op.residual;
     auto load_res = [&](int n) -> float {
@@ -321,8 +392,16 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
         }
         occ[warp] = ready;
     }
+    // Fragment mapping (mma.m16n8k16, weights as the A operand): the 16 bytes thread (g, t) reads from a ring item are 8 consecutive k
+    // of weight row g = four bf16 pairs P0..P3, used as a0..a3 = (row g, k-slot 0), (row g+8, slot 0), (row g, slot 1), (row g+8, slot 1):
+    // the upper 8 rows of the tile are weight row g again, with the OTHER half of the k values. The activation vector is staged with
+    // the pairs of each 8-k group reordered to [P0 P2 P1 P3] (x_perm), so column 0 of B (lanes g even) holds x for (P0, P2) and column 1
+    // (lanes g odd) x for (P1, P3): C[g][0] + C[g+8][1] is the dot product of row g over the 32-k chunk. One LDS.128 + one LDS.64
+    // per HMMA, no register shuffling, 512 weight bytes per HMMA (the first version used the weights as B: 256 bytes per HMMA plus
+    // four MOVs to duplicate x into both row halves, and the loop was HMMA-issue bound, profiles/r2_decode.md).
     const uint32_t ring_w = ptx::smem_u32(S.ring) + warp * (MG_SLOTS * MG_SLOT_BYTES) + g * 64 + t * 16;   // item: [chunk][row g][64 B]
-    const uint32_t x_u32 = ptx::smem_u32(S.xa) + t * 16;
+    const uint32_t x_u32 = ptx::smem_u32(S.xa) + t * 16 + (g & 1) * 8;
+    const uint32_t full_u32 = ptx::smem_u32(S.full) + warp * (MG_SLOTS * 8), empty_u32 = ptx::smem_u32(S.empty) + warp * (MG_SLOTS * 8);
     // The per-item partial sums of a CTA's units usually fit the `part` buffer at once (one pass). A phase whose item count exceeds it
     // (Llama-3's 128558-row lm_head: 109 units x 8 segments per CTA) runs in passes of `upp` units; upp * ipu is a multiple of 8, so
     // item q still belongs to warp q % 8, which is the order the producer lane of that warp streams them in.
@@ -334,41 +413,49 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     unsigned long long key = 0ull;
     long long wait_clk = 0;                                  // tracing only: cycles this warp spent waiting for ring items, items consumed
     int n_waited = 0;
+    // ring position and k segment are carried incrementally (no division per item): item q covers segment q % nseg
+    uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
+    const int seg_bytes = op.seg_len * 2, seg_step = MG_CONSUMERS % nseg;
+    const int nquad = op.seg_len / 128, tail2 = (op.seg_len / 64) & 1;     // chunks of 32 k: 4 per quad + one optional pair
+    float* const part_w = S.part + g;
     for (int u0 = 0; u0 < nu; u0 += upp) {
         const int nu_p = min(upp, nu - u0);
         const int q_lo = u0 * ipu, q_hi = (u0 + nu_p) * ipu;
+        int seg = (q_lo + warp) % nseg;
         for (int q = q_lo + warp; q < q_hi; q += MG_CONSUMERS) {
-            const uint32_t slot = cnt % MG_SLOTS, par = (cnt / MG_SLOTS) & 1;
             const long long w0 = occ ? clock64() : 0;
-            ptx::mbar_wait(ptx::smem_u32(&S.full[warp * MG_SLOTS + slot]), par);
+            ptx::mbar_wait(full_u32 + slot * 8, par);
             if (occ) { wait_clk += clock64() - w0; ++n_waited; }
-            const int j = q / ipu, r = q - j * ipu;
-            const int seg = r % nseg;
             uint32_t wa = ring_w + slot * MG_SLOT_BYTES;
-            uint32_t xa = x_u32 + seg * op.seg_len * 2;
+            uint32_t xa = x_u32 + seg * seg_bytes;
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
 #pragma unroll 2
-            for (int ch = 0; ch < nchunk2; ++ch) {
-                const uint4 w0 = lds128(wa), x0 = lds128(xa);
-                const uint4 w1 = lds128(wa + 512), x1 = lds128(xa + 64);
-                mma16816(acc[0], x0.x, x0.x, x0.y, x0.y, w0.x, w0.y);
-                mma16816(acc[1], x0.z, x0.z, x0.w, x0.w, w0.z, w0.w);
-                mma16816(acc[2], x1.x, x1.x, x1.y, x1.y, w1.x, w1.y);
-                mma16816(acc[3], x1.z, x1.z, x1.w, x1.w, w1.z, w1.w);
-                wa += 1024;
-                xa += 128;
+            for (int ch = 0; ch < nquad; ++ch) {
+                const uint4 w0 = lds128(wa), w1 = lds128(wa + 512), w2 = lds128(wa + 1024), w3 = lds128(wa + 1536);
+                const uint2 x0 = lds64(xa), x1 = lds64(xa + 64), x2 = lds64(xa + 128), x3 = lds64(xa + 192);
+                mma16816(acc[0], w0.x, w0.y, w0.z, w0.w, x0.x, x0.y);
+                mma16816(acc[1], w1.x, w1.y, w1.z, w1.w, x1.x, x1.y);
+                mma16816(acc[2], w2.x, w2.y, w2.z, w2.w, x2.x, x2.y);
+                mma16816(acc[3], w3.x, w3.y, w3.z, w3.w, x3.x, x3.y);
+                wa += 2048;
+                xa += 256;
             }
-            if (g == 0) {
-                float2 o;
-                o.x = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-                o.y = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-                *reinterpret_cast<float2*>(S.part + (size_t)(q - q_lo) * 8 + 2 * t) = o;
+            if (tail2) {
+                const uint4 w0 = lds128(wa), w1 = lds128(wa + 512);
+                const uint2 x0 = lds64(xa), x1 = lds64(xa + 64);
+                mma16816(acc[0], w0.x, w0.y, w0.z, w0.w, x0.x, x0.y);
+                mma16816(acc[1], w1.x, w1.y, w1.z, w1.w, x1.x, x1.y);
             }
+            if (t == 0)
+                part_w[(q - q_lo) * 8] = ((acc[0][0] + acc[0][3]) + (acc[1][0] + acc[1][3])) + ((acc[2][0] + acc[2][3]) + (acc[3][0] + acc[3][3]));
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&S.empty[warp * MG_SLOTS + slot]));
+            if (lane == 0) ptx::mbar_arrive(empty_u32 + slot * 8);
             ++cnt;
+            if (++slot == MG_SLOTS) { slot = 0; par ^= 1; }
+            seg += seg_step;
+            if (seg >= nseg) seg -= nseg;
         }
         cbar();
         // ---- epilogue of this pass: one thread per output column, segments summed in a fixed order
@@ -863,7 +950,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         for (int l = 0; l < P.n_layers; ++l) {
             long long* occ = (tracing && l == P.n_layers - 1) ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
             // norm + qkv
-            stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane);
+            stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane, occ ? occ + 96 : nullptr);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ);
             op = P.ops[l * 4 + 1];
@@ -873,14 +960,14 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
             tr.mark(tid); boundary(); tr.mark(tid);
             // merge + o_proj + residual
-            stage_x_attn(P, S, pos + 1, tid);
+            stage_x_attn<D>(P, S, pos + 1, tid, occ ? occ + 96 + 8 : nullptr);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 8 : nullptr);
             op = P.ops[l * 4 + 2];
             prefetch_norm(op, np, tid);
             tr.mark(tid); boundary(); tr.mark(tid);
             // norm + gate_up + SwiGLU
-            stage_x_vec(op, op.x, np, S, tid, warp, lane);
+            stage_x_vec(op, op.x, np, S, tid, warp, lane, occ ? occ + 96 + 16 : nullptr);
             tr.mark(tid);
             gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 16 : nullptr);
             op = P.ops[l * 4 + 3];
@@ -990,6 +1077,7 @@ bool decode_mega_finalize(MegaPlan* p) {
         long cap = avail / 32;
         if (cap < 64) return false;
         p->part_items = items < cap ? items : (int)cap;
+        if (p->part_items < 64) p->part_items = 64;          // stage_x_attn keeps its 2 KB of softmax weights here
     }
     p->att_maxp = G / H + 2;
     return (size_t)MG_RING_BYTES + p->x_bytes + (size_t)p->part_items * 32 <= (size_t)MG_SMEM_LIMIT;

@@ -52,6 +52,29 @@ def main():
     print("mode mega=%s  ctx=%d layers=%d: prefill %.2f ms, decode %.3f ms/step  -> %.0f GB/s (%.1f%% of %.0f)" % (
         os.environ.get("GVL_DECODE_MEGA", "1"), ctx, layers, pre, per_step, (wbytes + kvb) / per_step / 1e6,
         100 * (wbytes + kvb) / per_step / 1e6 / peak, peak))
+    # the decode launch alone, repeated: (generate - prefill) above is ONE sample taken right after a tensor-bound prefill and moves
+    # by +-10 % with the power state; here every repetition re-prefills, lets the GPU settle, and times gvl_lm_decode by itself
+    reps = int(os.environ.get("GVL_PROBE_REPS", "7"))
+    toks = torch.zeros(steps + 1, dtype=torch.int64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    samples = []
+    for _ in range(reps):
+        lm.prefill(emb, n_new=steps + 1)
+        handle = lm._active[0]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.gvl_lm_decode(handle, steps, ctypes.c_void_p(toks.data_ptr()), ctypes.c_void_p(0), -1, 0, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        assert rc == 0, rc
+        samples.append(e0.elapsed_time(e1) / steps)
+    samples.sort()
+    med, best = samples[len(samples) // 2], samples[0]
+    nbytes = wbytes + kvb
+    print("decode launch alone, %d repetitions of %d steps: median %.3f ms/step (%.1f%% of %.0f GB/s), best %.3f (%.1f%%), all %s" % (
+        reps, steps, med, 100 * nbytes / med / 1e6 / peak, peak, best, 100 * nbytes / best / 1e6 / peak,
+        " ".join("%.3f" % v for v in samples)))
     if os.environ.get("GVL_MEGA_TRACE"):
         handle = lm._active[0]
         buf = np.zeros((160, 1024), dtype=np.int64)
@@ -61,6 +84,8 @@ def main():
             print("trace unavailable rc=%d" % rc)
             return
         t = buf[: n.value].astype(np.float64)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "decode_trace_raw.npy"), buf[: n.value])
         L = layers
         # marks: 0 start | embed: done, passed | per layer 5 phases x (staged, done, passed) | lm_head x 3
         names = ["qkv", "attn", "o_proj", "gate_up", "down"]
@@ -93,6 +118,9 @@ def main():
         ni = buf[: n.value, 832:864].reshape(n.value, 4, 8).astype(np.float64)
         print("  last layer, per consumer warp: cycles spent WAITING for ring items / items consumed / phase work cycles (mean over CTAs x warps): "
               + ", ".join("%s %.0f / %.1f" % (k, wt[:, i].mean(), ni[:, i].mean()) for i, k in enumerate(["qkv", "o_proj", "gate_up", "down"])))
+        sm = buf[: n.value, 864:888].reshape(n.value, 3, 8)[:, :, :4].astype(np.float64)
+        print("  staging of the last layer (cycles, mean over CTAs): entry -> loads in registers -> CTA barrier -> written: "
+              + ", ".join("%s %s" % (k, np.diff(sm[:, i], axis=1).mean(0).astype(int).tolist()) for i, k in enumerate(["qkv", "attn_merge", "gate_up"])))
         a = buf[: n.value, 960:1024].reshape(n.value, 8, 8).astype(np.float64)
         d = np.diff(a, axis=2)                                   # [cta, warp, 7]
         tot = a[:, :, 7] - a[:, :, 0]
