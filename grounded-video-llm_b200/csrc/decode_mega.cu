@@ -51,12 +51,24 @@ constexpr int MG_ATT_SHORT = 128;                                // ctx <= this:
 // exactly these items (round-1 sweep of (ahead, current): (1,1) 2.50 (1,2) 2.57 (1,3) 2.52 (2,3) 2.47 ms / step)
 constexpr int MG_INFLIGHT_AHEAD = 1, MG_INFLIGHT_CUR = MG_SLOTS;
 
-__host__ __device__ inline int att_warp_len(int ctx, int H, int G) {
-    if (ctx <= MG_ATT_SHORT) return ctx;
-    const int TW = G * MG_CONSUMERS;
-    const int per = (H * ctx + TW - 1) / TW;
-    return (per + 7) & ~7;
+// Split of the attention phase over the grid's consumer warps: every head gets the same number of warps (wph = 37 for 148 SMs and
+// 32 heads) and every warp ONE contiguous token range of ONE head, <= lw tokens. The first version cut the flat (head, token) space
+// evenly instead; a warp that straddled two heads then streamed two short segments = 8 ring items instead of 6, and with 3 slots per
+// warp and ~5k cycles of bulk-copy latency under load an item costs a third of a round trip whatever its size: those 32 warps took
+// 22k cycles against 12k and the whole grid waited for them at the barrier (profiles/r2_decode.md).
+struct AttSplit {
+    int wph, lw;        // warps per head, tokens per warp (multiple of 8)
+};
+__host__ __device__ inline AttSplit att_split(int ctx, int H, int G) {
+    AttSplit a;
+    if (ctx <= MG_ATT_SHORT) { a.wph = 1; a.lw = ctx; return a; }          // one warp per head
+    a.wph = (G * MG_CONSUMERS) / H;
+    a.lw = (((ctx + a.wph - 1) / a.wph) + 7) & ~7;
+    return a;
 }
+// CTAs whose warps work on head h: [att_c0, att_c1]
+__host__ __device__ inline int att_c0(int h, int wph) { return (h * wph) / MG_CONSUMERS; }
+__host__ __device__ inline int att_c1(int h, int wph) { return (h * wph + wph - 1) / MG_CONSUMERS; }
 __host__ __device__ inline int att_scratch_bytes(int D) { return MG_CONSUMERS * 2 * D * 4 + 2 * MG_CONSUMERS * (D + 4) * 4; }
 // K / V rows of a (head, token range) are contiguous in the cache, so they travel through the same per-warp rings as the
 // weights: a segment of `len` cached tokens is cut evenly into chunks of <= ct_max tokens (one ring slot), multiple of 8
@@ -257,7 +269,7 @@ template <int D>
 __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, int ctx, int tid, long long* sm = nullptr) {
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(S.xa);
     const int H = P.heads, D4 = D + 4, maxp = P.att_maxp;
-    const int Lc = att_warp_len(ctx, H, gridDim.x) * MG_CONSUMERS;
+    const int wph = att_split(ctx, H, gridDim.x).wph;
     if (sm != nullptr && tid == 0) sm[0] = clock64();
     constexpr int NS = 6, NG = D / 32;
     if (maxp <= NS && H <= 32) {
@@ -265,7 +277,7 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
         const int h1 = tid >> 3, s1 = tid & 7;
         float2 hd1 = make_float2(-INFINITY, 0.f);
         if (h1 < H) {
-            const int c0 = (h1 * ctx) / Lc, c1 = ((h1 + 1) * ctx - 1) / Lc;
+            const int c0 = att_c0(h1, wph), c1 = att_c1(h1, wph);
             if (s1 <= c1 - c0) hd1 = __ldcg(reinterpret_cast<const float2*>(P.att_ws + ((size_t)h1 * maxp + s1) * D4));
         }
         float4 ov[NG][NS];
@@ -275,7 +287,7 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
             const bool live = h < H;
             int np = 0;
             if (live) {
-                const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+                const int c0 = att_c0(h, wph), c1 = att_c1(h, wph);
                 np = c1 - c0 + 1;
             }
             const float* base = P.att_ws + (size_t)h * maxp * D4 + 4 + d0;
@@ -314,7 +326,7 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
     }
     for (int gi = tid; gi < H * D / 4; gi += 256) {
         const int e0 = gi * 4, h = e0 / D, d0 = e0 - h * D;
-        const int c0 = (h * ctx) / Lc, c1 = ((h + 1) * ctx - 1) / Lc;
+        const int c0 = att_c0(h, wph), c1 = att_c1(h, wph);
         const int np = c1 - c0 + 1;
         const float* base = P.att_ws + (size_t)h * maxp * D4;
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -558,32 +570,21 @@ __device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, 
     const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
     const int G = gridDim.x, c = blockIdx.x;
     const int ctx = pos + 1;
-    const int Lw = att_warp_len(ctx, H, G);
-    const int total = H * ctx;
+    const AttSplit sp = att_split(ctx, H, G);
     const __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
     const __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
-    int f = 0, f1 = 0;
-    if (lane < MG_CONSUMERS) {
-        f = (c * MG_CONSUMERS + lane) * Lw;
-        f1 = min(f + Lw, total);
-    }
     int tb = 0, tend = 0, cs = 8, hk = 0, is_v = 0;
-    auto next_seg = [&]() -> bool {
-        while (f < f1) {
-            const int h = f / ctx;
-            const int t0 = f - h * ctx;
-            const int t1 = min(ctx, t0 + (f1 - f));
-            f += t1 - t0;
-            const int te = min(t1, pos);                 // the new token (pos) never comes from the cache
-            if (te > t0) {
-                tb = t0; tend = te; hk = h / rep; is_v = 0;
-                cs = att_chunk_len(te - t0, CTM);
-                return true;
-            }
+    bool active = false;
+    if (lane < MG_CONSUMERS) {
+        const int gw = c * MG_CONSUMERS + lane, h = gw / sp.wph;
+        const int t0 = (gw - h * sp.wph) * sp.lw;
+        const int te = min(min(ctx, t0 + sp.lw), pos);       // the new token (pos) never comes from the cache
+        if (h < H && te > t0) {
+            tb = t0; tend = te; hk = h / rep;
+            cs = att_chunk_len(te - t0, CTM);
+            active = true;
         }
-        return false;
-    };
-    bool active = next_seg();
+    }
     const uint32_t ring_w = ptx::smem_u32(S.ring) + lane * (MG_SLOTS * MG_SLOT_BYTES);
     const uint32_t full0 = ptx::smem_u32(S.full + lane * MG_SLOTS), empty0 = ptx::smem_u32(S.empty + lane * MG_SLOTS);
     // Rows appended by the previous step of this launch are part of this stream: wait until this CTA's consumers are past
@@ -613,7 +614,7 @@ __device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, 
                 if (is_v) {
                     tb += cs;
                     is_v = 0;
-                    if (tb >= tend) active = next_seg();
+                    if (tb >= tend) active = false;
                 } else {
                     is_v = 1;
                 }
@@ -632,8 +633,7 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
     const int H = P.heads, KVH = P.kv_heads, rep = H / KVH;
     const int G = gridDim.x, c = blockIdx.x;
     const int ctx = pos + 1;
-    const int Lw = att_warp_len(ctx, H, G), Lc = Lw * MG_CONSUMERS;
-    const int total = H * ctx;
+    const AttSplit sp = att_split(ctx, H, G);
     const __nv_bfloat16* qkv = P.qkv;
     __nv_bfloat16* kc_l = P.kv + (size_t)layer * 2 * KVH * P.max_ctx * D;
     __nv_bfloat16* vc_l = kc_l + (size_t)KVH * P.max_ctx * D;
@@ -651,14 +651,12 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
 #define ATR(k) do { if (atr) atr[k] = clock64(); } while (0)
     ATR(0);
     if (lane < 2) segs[(warp * 2 + lane) * D4] = __int_as_float(-1);
-    const int f0 = (c * MG_CONSUMERS + warp) * Lw;
-    const int f1 = min(f0 + Lw, total);
-    int f = f0, sg = 0;
-    while (f < f1) {
-        const int h = f / ctx, hk = h / rep;
-        const int t0 = f - h * ctx;
-        const int t1 = min(ctx, t0 + (f1 - f));
-        f += t1 - t0;
+    const int gw = c * MG_CONSUMERS + warp;
+    const int h = gw / sp.wph, hk = h / rep;
+    const int t0 = (gw - h * sp.wph) * sp.lw;
+    const int t1 = min(ctx, t0 + sp.lw);
+    int sg = 0;
+    if (h < H && t0 < t1) {
         // ---- RoPE of q (and of the new k) for this head: q_embed = bf16(bf16(q*cos) + bf16(rot(q)*sin))
         __syncwarp();
         {
@@ -840,9 +838,9 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
     cbar();
     ATR(6);
     // ---- merge the warp segments of this CTA per head, one global partial per (head, CTA)
-    const int cf0 = c * Lc, cf1 = min(cf0 + Lc, total);
-    if (cf0 < cf1) {
-        const int h_first = cf0 / ctx, h_last = (cf1 - 1) / ctx;
+    // (a CTA whose warps of head hh have no tokens still writes its record: max = -inf, sum = 0, which stage_x_attn weighs with 0)
+    {
+        const int h_first = (c * MG_CONSUMERS) / sp.wph, h_last = min(H - 1, (c * MG_CONSUMERS + MG_CONSUMERS - 1) / sp.wph);
         for (int hh = h_first + warp; hh <= h_last; hh += MG_CONSUMERS) {
             float M = -INFINITY;
             for (int s = 0; s < 2 * MG_CONSUMERS; ++s)
@@ -861,7 +859,7 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
                     if (d < D) num[i] += w * segs[s * D4 + 4 + d];
                 }
             }
-            const int c0 = (hh * ctx) / Lc;
+            const int c0 = att_c0(hh, sp.wph);
             float* dst = P.att_ws + ((size_t)hh * P.att_maxp + (c - c0)) * D4;
 #pragma unroll
             for (int i = 0; i < (D + 31) / 32; ++i) {
