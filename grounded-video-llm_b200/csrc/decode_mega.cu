@@ -44,7 +44,7 @@ constexpr int MG_THREADS = 32 * (MG_CONSUMERS + 1);          // 8 consumer warps
 constexpr int MG_SLOT_BYTES = MEGA_ROWS * MEGA_SEG * 2;          // 8192: one packed item
 constexpr int MG_SLOTS = 3;                                      // ring depth per consumer warp
 constexpr int MG_RING_BYTES = MG_CONSUMERS * MG_SLOTS * MG_SLOT_BYTES;   // 196608
-constexpr int MG_SMEM_LIMIT = 232448 - 2048;                     // 227 KB opt-in minus static shared memory
+constexpr int MG_SMEM_LIMIT = 232448 - 3072;                     // 227 KB opt-in minus static shared memory
 constexpr int MG_ATT_SHORT = 128;                                // ctx <= this: one warp per head
 // bulk copies each producer lane keeps outstanding: 1 while its phase is still ahead of the consumers (pure prefetch: tools/probe_exchange.cu
 // measured 8-22 us per grid-wide exchange with 2-3 copies per lane queued against 4 us with one), all slots once the consumers wait for
