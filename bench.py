@@ -311,7 +311,26 @@ def run_gvl_arm(args):
     torch.cuda.synchronize()
     clean_enc_ms, clean_pre_ms = dv[2].elapsed_time(dv[3]), dv[3].elapsed_time(dv[4])
     dec_steps = DECODE_TOKENS - 1                                     # the first token comes out of the prefill
-    dec_step_ms = (dv[1].elapsed_time(dv[2]) - dv[0].elapsed_time(dv[1])) / dec_steps
+    dec_step_diff_ms = (dv[1].elapsed_time(dv[2]) - dv[0].elapsed_time(dv[1])) / dec_steps
+    # The difference above is ONE sample taken right after a tensor-bound prefill; it moves by +-10 % with the power state (2.3 - 2.9 ms
+    # for the same binary inside one job, profiles/r2_decode.md). The roofline figure is therefore the decode launch timed BY ITSELF:
+    # prefill (untimed) -> CUDA events around gvl_lm_decode(15 steps), 5 repetitions, median.
+    dec_samples = []
+    dtoks = torch.zeros(DECODE_TOKENS, dtype=torch.int64, device=dev)
+    cur_stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(5):
+        m.language_model.prefill(emb[0], n_new=DECODE_TOKENS)
+        handle = m.language_model._active[0]
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        rc = lib.gvl_lm_decode(handle, dec_steps, ctypes.c_void_p(dtoks.data_ptr()), ctypes.c_void_p(0), -1, 0, cur_stream)
+        d1.record()
+        torch.cuda.synchronize()
+        assert rc == 0, rc
+        dec_samples.append(d0.elapsed_time(d1) / dec_steps)
+    dec_samples.sort()
+    dec_step_ms = dec_samples[len(dec_samples) // 2]
     dec_bytes = DECODE_BYTES_WEIGHTS + (emb.shape[1] + dec_steps / 2.0) * KV_BYTES_PER_CTX_TOKEN
     pk = _peaks()
     if rank == 0:
@@ -348,7 +367,10 @@ def run_gvl_arm(args):
                        "traffic_bytes_per_step_ncu": 8.90e9,   # dram__bytes_read of one captured launch / its 8 steps (profiles/r1_decode_mega_ncu_metrics.csv)
                        "kernel": "gvl::decode_mega_kernel<96> (one persistent launch per generate call; GVL_DECODE_MEGA=0: per-op chain)"
                                  if os.environ.get("GVL_DECODE_MEGA", "1") != "0" else "per-op chain: gemv3_kernel + decode_attn_kernel (CUDA graph)",
-                       "how": "CUDA events: (prefill + %d-token generate) - prefill, / %d steps; bytes = 7.447 GB weights + ctx x 393 KB K/V" % (DECODE_TOKENS, dec_steps)},
+                       "samples_ms_per_step": dec_samples, "ms_per_step_generate_minus_prefill": dec_step_diff_ms,
+                       "how": "CUDA events around the decode launch alone (gvl_lm_decode, %d steps, after an untimed prefill), median of 5; "
+                              "(prefill + %d-token generate) - prefill is reported beside it; bytes = 7.447 GB weights + ctx x 393 KB K/V"
+                              % (dec_steps, DECODE_TOKENS)},
             "gemv_launches_profiled": {"ms": v_ms, "launches": v_n},
             "e2e_from_raw_frames": {"value": B * args.steps / (raw_ms * 1e-3), "unit": UNIT, "ms_per_step": raw_ms / args.steps,
                                     "h2d_bytes_per_step": B * 96 * 3 * 336 * 336 + B * T_TEXT * 8,

@@ -67,16 +67,14 @@ __device__ __forceinline__ void da_finish(float* ws, int* counters, __nv_bfloat1
 
 // grid (heads, max_splits). 4 lanes share one token (D/4 elements each); 32 tokens per CTA iteration.
 template <int D>
-__global__ void __launch_bounds__(DA_THREADS)
-decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                   const __nv_bfloat16* __restrict__ vc, float* ws, const int* __restrict__ ctx_len_dev,
-                   int heads, int kv_heads, int max_ctx, float scale, int* counters, __nv_bfloat16* o_out) {
+__device__ __forceinline__ void
+decode_attn_body(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                 const __nv_bfloat16* __restrict__ vc, float* ws, const int* __restrict__ ctx_len_dev,
+                 int heads, int kv_heads, int max_ctx, float scale, int* counters, __nv_bfloat16* o_out, int split, int nsplit) {
     constexpr int EPL = D / 4;  // elements per lane
     constexpr int VPL = EPL / 8;
-    pdl_launch_dependents();
-    pdl_wait();
     const int ctx = *ctx_len_dev;  // tokens in the cache INCLUDING the one appended this step
-    const int h = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+    const int h = blockIdx.x;
     const int hk = h / (heads / kv_heads);
     const int t0 = split * DA_CHUNK;
     float* wrow = ws + ((size_t)h * nsplit + split) * (D + 2);
@@ -205,6 +203,30 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     da_finish<D>(ws, counters, o_out, h, nsplit, tid);
 }
 
+template <int D>
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                   const __nv_bfloat16* __restrict__ vc, float* ws, const int* __restrict__ ctx_len_dev,
+                   int heads, int kv_heads, int max_ctx, float scale, int* counters, __nv_bfloat16* o_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    decode_attn_body<D>(q, kc, vc, ws, ctx_len_dev, heads, kv_heads, max_ctx, scale, counters, o_out, blockIdx.y, gridDim.y);
+}
+
+// the same step for up to 4 sequences in ONE launch (gvl_lm_decode_batch): grid (heads, max splits, sequences); every sequence has
+// its own cache, context length, workspace and split count (a function of ITS max_ctx)
+template <int D>
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_batch_kernel(DecodeAttnBatch b, int heads, int kv_heads, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const DecodeAttnSeq& p = b.s[blockIdx.z];
+    const int nsplit = (p.max_ctx + DA_CHUNK - 1) / DA_CHUNK;
+    if ((int)blockIdx.y >= nsplit) return;
+    decode_attn_body<D>(p.q, p.kc, p.vc, p.ws, p.ctx_len, heads, kv_heads, p.max_ctx, scale,
+                        reinterpret_cast<int*>(p.ws + (size_t)heads * nsplit * (D + 2)), p.o, blockIdx.y, nsplit);
+}
+
 // ---------------------------------------------------------------- greedy sampling / step state
 // first maximal index (torch.argmax tie order); single CTA.
 __global__ void __launch_bounds__(1024)
@@ -250,14 +272,12 @@ __global__ void embed_token_kernel(const __nv_bfloat16* __restrict__ table, cons
 }
 
 // RoPE for the single new token at position ctx_len (before increment), append k,v to the cache.
-__global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+__device__ __forceinline__ void rope_decode_body(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
                                    __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
                                    const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
                                    const DecodeState* __restrict__ st, int heads, int kv_heads, int D, int max_ctx) {
     const int half = D / 2;
     const int total = (heads + 2 * kv_heads) * half;
-    pdl_launch_dependents();
-    pdl_wait();
     const int pos = st->ctx_len;  // slot == position (single unpadded sequence)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int hh = i / half, j = i % half;
@@ -281,6 +301,22 @@ __global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_b
             dst[j] = src[j]; dst[j + half] = src[j + half];
         }
     }
+}
+
+__global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ q_out,
+                                   __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                                   const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
+                                   const DecodeState* __restrict__ st, int heads, int kv_heads, int D, int max_ctx) {
+    pdl_launch_dependents();
+    pdl_wait();
+    rope_decode_body(qkv, q_out, k_cache, v_cache, cosb, sinb, st, heads, kv_heads, D, max_ctx);
+}
+// grid (blocks, sequences): every sequence rotates with ITS position and RoPE table and appends to ITS cache
+__global__ void rope_decode_batch_kernel(DecodeRopeBatch b, int heads, int kv_heads, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const DecodeRopeSeq& p = b.s[blockIdx.y];
+    rope_decode_body(p.qkv, p.q_out, p.k_cache, p.v_cache, p.cosb, p.sinb, p.st, heads, kv_heads, D, p.max_ctx);
 }
 
 // After the per-layer rope kernels of a step: attention must see ctx_len+1 tokens. We keep two counters:
@@ -360,6 +396,28 @@ int decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kc, const __nv
     else return GVL_ERR_ARG;
     g_launch_count++;
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int decode_attention_batch(const DecodeAttnBatch& b, int n_seq, int heads, int kv_heads, int head_dim, float scale, cudaStream_t s) {
+    if (n_seq < 1 || n_seq > 4) return GVL_ERR_ARG;
+    int nsplit = 1;
+    for (int i = 0; i < n_seq; ++i) nsplit = max(nsplit, (b.s[i].max_ctx + DA_CHUNK - 1) / DA_CHUNK);
+    dim3 grid(heads, nsplit, n_seq);
+    cudaError_t e;
+    if (head_dim == 64) e = launch_k(decode_attn_batch_kernel<64>, grid, dim3(DA_THREADS), 0, s, b, heads, kv_heads, scale);
+    else if (head_dim == 96) e = launch_k(decode_attn_batch_kernel<96>, grid, dim3(DA_THREADS), 0, s, b, heads, kv_heads, scale);
+    else if (head_dim == 128) e = launch_k(decode_attn_batch_kernel<128>, grid, dim3(DA_THREADS), 0, s, b, heads, kv_heads, scale);
+    else return GVL_ERR_ARG;
+    g_launch_count++;
+    return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? GVL_OK : GVL_ERR_CUDA;
+}
+
+int rope_decode_batch(const DecodeRopeBatch& b, int n_seq, int heads, int kv_heads, int D, cudaStream_t s) {
+    if (n_seq < 1 || n_seq > 4) return GVL_ERR_ARG;
+    const int total = (heads + 2 * kv_heads) * (D / 2);
+    launch_k(rope_decode_batch_kernel, dim3((total + 255) / 256, n_seq), dim3(256), 0, s, b, heads, kv_heads, D);
+    g_launch_count++;
+    return cudaGetLastError() == cudaSuccess ? GVL_OK : GVL_ERR_CUDA;
 }
 
 int argmax_f32(const float* logits, int n, long long* out, cudaStream_t s) {

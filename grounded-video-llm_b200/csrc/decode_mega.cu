@@ -390,6 +390,7 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
     auto load_res = [&](int n) -> float {
         return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(res) + n) << 16);
     };
+    if (occ != nullptr && tid == 0) occ[128] = clock64();        // tracing: entry / item loop done / CTA barrier passed / epilogue done
     float res_pre = 0.f;
     if (res != nullptr && tid < nu * MEGA_ROWS) {
         const int n = (c + (tid >> 3) * G) * MEGA_ROWS + (tid & 7);
@@ -469,7 +470,9 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
             seg += seg_step;
             if (seg >= nseg) seg -= nseg;
         }
+        if (occ != nullptr && tid == 0) occ[129] = clock64();
         cbar();
+        if (occ != nullptr && tid == 0) occ[130] = clock64();
         // ---- epilogue of this pass: one thread per output column, segments summed in a fixed order
         for (int o0 = 0; o0 < nu_p * MEGA_ROWS; o0 += 256) {
             const int o = o0 + tid;
@@ -509,6 +512,7 @@ __device__ __forceinline__ void gemv_items(const MegaOp& op, const MegaPlan& P, 
         if (u0 + upp < nu) cbar();                       // the next pass overwrites the partial sums
     }
     if (occ != nullptr && lane == 0) { occ[32 + warp] = wait_clk; occ[64 + warp] = n_waited; }
+    if (occ != nullptr && tid == 0) occ[131] = clock64();
     if (op.argmax) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -31,7 +31,8 @@ struct MegaOp {                 // one weight-streaming GEMV phase (M = 1)
 constexpr int MEGA_MAX_LAYERS = 48;
 constexpr int MEGA_TRACE_STRIDE = 1024;  // clock64 marks per CTA per step: 3 + 15 * layers + 3 (layers <= 48 -> 726)
 constexpr int MEGA_TRACE_OCC_OFF = 768;  // + 4 GEMV phases of the last layer x 8 warps: ring slots already landed at phase start;
-                                         // + 32: cycles the warp waited for ring items in that phase; + 64: items it consumed
+                                         // + 32: cycles the warp waited for ring items in that phase; + 64: items it consumed;
+                                         // + 96: 3 staging steps x 4 marks (stride 8); + 128: 4 GEMV phases x 4 marks (stride 8)
 constexpr int MEGA_TRACE_ATT_OFF = 960;  // + 8 warps x 8 marks inside the attention phase of the last layer;
                                          // [ATT_OFF - 2], [ATT_OFF - 1]: %globaltimer (ns) at kernel start / end
 

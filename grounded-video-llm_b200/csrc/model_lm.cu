@@ -416,13 +416,18 @@ static int enqueue_batch_step(gvl_lm* const* lms, int n, long long eos_id, long 
         const gvl_lm_layer& L = L0->layers[l];
         CK(gemv_bf16(L0->bx, D, (const __nv_bfloat16*)L.qkv_w, D, L0->bqkv, qkv_n, n, qkv_n, D, (const __nv_bfloat16*)L.in_norm_w,
                      w.rms_eps, nullptr, nullptr, 0, 0, 0, s));
+        // RoPE + append and the split-KV attention of ALL sequences in one launch each (own cache / position / workspace per sequence)
+        DecodeRopeBatch rb = {};
+        DecodeAttnBatch ab = {};
         for (int b = 0; b < n; ++b) {
             gvl_lm* m = lms[b];
-            CK(rope_decode(L0->bqkv + (size_t)b * qkv_n, L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l),
-                           (const __nv_bfloat16*)m->w.rope_cos, (const __nv_bfloat16*)m->w.rope_sin, m->st, H, KVH, hd, m->w.max_ctx, s));
-            CK(decode_attention(L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l), L0->battn + (size_t)b * HD, m->da_ws,
-                                &m->st->attn_len, H, KVH, hd, m->w.max_ctx, scale, s));
+            rb.s[b] = {L0->bqkv + (size_t)b * qkv_n, L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l),
+                       (const __nv_bfloat16*)m->w.rope_cos, (const __nv_bfloat16*)m->w.rope_sin, m->st, m->w.max_ctx};
+            ab.s[b] = {L0->bq + (size_t)b * HD, m->kcache(l), m->vcache(l), L0->battn + (size_t)b * HD, m->da_ws, &m->st->attn_len,
+                       m->w.max_ctx};
         }
+        CK(rope_decode_batch(rb, n, H, KVH, hd, s));
+        CK(decode_attention_batch(ab, n, H, KVH, hd, scale, s));
         CK(gemv_bf16(L0->battn, HD, (const __nv_bfloat16*)L.o_w, HD, L0->bx, D, n, D, HD, nullptr, 0.f, nullptr, L0->bx, D, 0, 0, s));
         CK(gemv_bf16(L0->bx, D, (const __nv_bfloat16*)L.gate_up_w, D, L0->bmid, F, n, 2 * F, D, (const __nv_bfloat16*)L.post_norm_w,
                      w.rms_eps, nullptr, nullptr, 0, 3, 0, s));
@@ -512,7 +517,7 @@ int gvl_lm_decode_batch(gvl_lm* const* lms, int n_seq, int n_steps, long long* t
         L0->b_n = n_seq; L0->b_logits = want_logits; L0->b_eos = eos_id; L0->b_pad = pad_id;
         for (int b = 0; b < 4; ++b) L0->b_members[b] = b < n_seq ? lms[b] : nullptr;
     }
-    const long long per_step = 2LL * n_seq + (long long)w.n_layers * (4 + 2 * n_seq) + 1 + n_seq;
+    const long long per_step = 2LL * n_seq + (long long)w.n_layers * (4 + 2) + 1 + n_seq;
     for (int i = 0; i < n_steps; ++i) {
         CU(cudaGraphLaunch(L0->bgraph, s));
         g_launch_count += per_step;

@@ -121,6 +121,9 @@ def main():
         sm = buf[: n.value, 864:888].reshape(n.value, 3, 8)[:, :, :4].astype(np.float64)
         print("  staging of the last layer (cycles, mean over CTAs): entry -> loads in registers -> CTA barrier -> written: "
               + ", ".join("%s %s" % (k, np.diff(sm[:, i], axis=1).mean(0).astype(int).tolist()) for i, k in enumerate(["qkv", "attn_merge", "gate_up"])))
+        gm = buf[: n.value, 896:928].reshape(n.value, 4, 8)[:, :, :4].astype(np.float64)
+        print("  GEMV phases of the last layer, warp 0 (cycles, mean over CTAs): entry -> item loop done -> CTA barrier -> epilogue done: "
+              + ", ".join("%s %s" % (k, np.diff(gm[:, i], axis=1).mean(0).astype(int).tolist()) for i, k in enumerate(["qkv", "o_proj", "gate_up", "down"])))
         a = buf[: n.value, 960:1024].reshape(n.value, 8, 8).astype(np.float64)
         d = np.diff(a, axis=2)                                   # [cta, warp, 7]
         tot = a[:, :, 7] - a[:, :, 0]
