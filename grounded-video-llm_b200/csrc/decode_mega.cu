@@ -949,44 +949,31 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
         NormPre np;
         prefetch_norm(op, np, tid);
         auto boundary = [&]() { grid_barrier(P.grid_bar, epoch, tid, &s_epoch); };
-        for (int l = 0; l < P.n_layers; ++l) {
+        // One loop over the GEMV phases (4 per layer: qkv | o_proj | gate_up | down, then lm_head), with the attention phase after
+        // every qkv: stage_x_* / gemv_items / attention_phase exist ONCE in the kernel. The first version spelled the layer out
+        // (5 inlined copies of the GEMV phase): 13.1k SASS instructions = 210 KB, and the ncu capture had 8 % of the warp samples on
+        // stall_no_inst in the once-per-layer boundary code (profiles/r2_decode.md).
+        for (int i = 0; i < n_ops; ++i) {
+            const int l = i >> 2, j = i & 3;
             long long* occ = (tracing && l == P.n_layers - 1) ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_OCC_OFF : nullptr;
-            // norm + qkv
-            stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane, occ ? occ + 96 : nullptr);
+            // input vector: merge of the attention partials (o_proj) or a vector in global memory (+ RMSNorm)
+            if (op.x_kind == 1) stage_x_attn<D>(P, S, pos + 1, tid, occ ? occ + 96 + 8 : nullptr);
+            else stage_x_vec(op, (op.from_embed & 1) ? emb_row : op.x, np, S, tid, warp, lane, occ ? occ + 96 + 8 * j : nullptr);
             tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ);
-            op = P.ops[l * 4 + 1];
+            gemv_items(op, P, emb_row, (i == n_ops - 1 && logits_out) ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane,
+                       occ ? occ + 8 * j : nullptr);
+            if (i + 1 < n_ops) {
+                op = P.ops[i + 1];
+                prefetch_norm(op, np, tid);
+            }
             tr.mark(tid); boundary(); tr.mark(tid);
-            // rope + KV append + split-KV attention
-            attention_phase<D>(P, l, pos, S, cnt, warp, lane);
-            tr.mark(tid);                               // keeps 3 marks per phase (no staging step here)
-            tr.mark(tid); boundary(); tr.mark(tid);
-            // merge + o_proj + residual
-            stage_x_attn<D>(P, S, pos + 1, tid, occ ? occ + 96 + 8 : nullptr);
-            tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 8 : nullptr);
-            op = P.ops[l * 4 + 2];
-            prefetch_norm(op, np, tid);
-            tr.mark(tid); boundary(); tr.mark(tid);
-            // norm + gate_up + SwiGLU
-            stage_x_vec(op, op.x, np, S, tid, warp, lane, occ ? occ + 96 + 16 : nullptr);
-            tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 16 : nullptr);
-            op = P.ops[l * 4 + 3];
-            tr.mark(tid); boundary(); tr.mark(tid);
-            // down + residual
-            stage_x_vec(op, op.x, np, S, tid, warp, lane);
-            tr.mark(tid);
-            gemv_items(op, P, emb_row, nullptr, S, cnt, tid, warp, lane, occ ? occ + 24 : nullptr);
-            op = P.ops[l * 4 + 4];
-            prefetch_norm(op, np, tid);
-            tr.mark(tid); boundary(); tr.mark(tid);
+            if (j == 0 && i + 1 < n_ops) {
+                // rope + KV append + split-KV attention
+                attention_phase<D>(P, l, pos, S, cnt, warp, lane);
+                tr.mark(tid);                           // keeps 3 marks per phase (no staging step here)
+                tr.mark(tid); boundary(); tr.mark(tid);
+            }
         }
-        // norm + lm_head + bias + greedy pick
-        stage_x_vec(op, op.x, np, S, tid, warp, lane);
-        tr.mark(tid);
-        gemv_items(op, P, emb_row, logits_out ? logits_out + (size_t)step * P.vocab : nullptr, S, cnt, tid, warp, lane);
-        tr.mark(tid); boundary(); tr.mark(tid);
         // ---- bookkeeping (CTA 0): tokens_out[step] = argmax (or pad after EOS), ctx_len++, step++
         if (blockIdx.x == 0 && tid == 0) {
             DecodeState* st = P.st;
