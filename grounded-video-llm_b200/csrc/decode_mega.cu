@@ -331,29 +331,7 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
         const float* base = P.att_ws + (size_t)h * maxp * D4;
         float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
         float den = 0.f;
-        if (np <= 8) {
-            float2 hd[8];
-            float4 ov[8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                if (s < np) {
-                    hd[s] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)s * D4));
-                    ov[s] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * D4 + 4 + d0));
-                } else {
-                    hd[s] = make_float2(-INFINITY, 0.f);
-                    ov[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            float M = hd[0].x;
-#pragma unroll
-            for (int s = 1; s < 8; ++s) M = fmaxf(M, hd[s].x);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const float w = __expf(hd[s].x - M);
-                den += w * hd[s].y;
-                num.x += w * ov[s].x; num.y += w * ov[s].y; num.z += w * ov[s].z; num.w += w * ov[s].w;
-            }
-        } else {
+        {
             float M = -INFINITY;
             for (int s = 0; s < np; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * D4));
 #pragma unroll 4
@@ -629,7 +607,7 @@ __device__ __forceinline__ void produce_attention(const MegaPlan& P, int layer, 
 }
 
 // ------------------------------------------------------------------ attention phase
-template <int D>
+template <int D, bool TRACE>
 __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, int pos, const Smem& S, uint32_t& cnt, int warp,
                                                 int lane) {
     constexpr int EPL = D / 4, VPL = EPL / 8, half = D / 2, D4 = D + 4;
@@ -650,7 +628,7 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
     const float scale = P.scale;
 
     // bring-up trace of the LAST layer: per-warp clock64 at 8 points of this phase (MEGA_TRACE_ATT_OFF + warp * 8 + k)
-    long long* atr = (P.trace && layer == P.n_layers - 1 && lane == 0)
+    long long* atr = (TRACE && layer == P.n_layers - 1 && lane == 0)
                          ? P.trace + (size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF + warp * 8 : nullptr;
 #define ATR(k) do { if (atr) atr[k] = clock64(); } while (0)
     ATR(0);
@@ -877,7 +855,8 @@ __device__ __forceinline__ void attention_phase(const MegaPlan& P, int layer, in
 #undef ATR
 }
 
-template <int D>
+// TRACE: the variant launched when MegaPlan::trace is set (GVL_MEGA_TRACE); the production variant carries no tracing code
+template <int D, bool TRACE>
 __global__ void __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* tokens_out, float* logits_out,
                    long long eos_id, long long pad_id) {
@@ -932,7 +911,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
     uint32_t cnt = 0;
     const int pos0 = P.st->ctx_len;                     // position == cache slot of the first token processed
     const int step0 = P.st->step;
-    const bool tracing = P.trace != nullptr;
+    constexpr bool tracing = TRACE;
     if (tracing && tid == 0) P.trace[(size_t)blockIdx.x * MEGA_TRACE_STRIDE + MEGA_TRACE_ATT_OFF - 2] = (long long)globaltimer_ns();
     for (int stp = 0; stp < n_steps; ++stp) {
         const int pos = pos0 + stp, step = step0 + stp;
@@ -969,7 +948,7 @@ decode_mega_kernel(const MegaPlan* __restrict__ plan_g, int n_steps, long long* 
             tr.mark(tid); boundary(); tr.mark(tid);
             if (j == 0 && i + 1 < n_ops) {
                 // rope + KV append + split-KV attention
-                attention_phase<D>(P, l, pos, S, cnt, warp, lane);
+                attention_phase<D, TRACE>(P, l, pos, S, cnt, warp, lane);
                 tr.mark(tid);                           // keeps 3 marks per phase (no staging step here)
                 tr.mark(tid); boundary(); tr.mark(tid);
             }
@@ -1080,9 +1059,12 @@ int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps
                        long long eos_id, long long pad_id, cudaStream_t s) {
     const size_t smem = (size_t)MG_RING_BYTES + hp->x_bytes + (size_t)hp->part_items * 32;
     using KernelT = void (*)(const MegaPlan*, int, long long*, float*, long long, long long);
-    const int di = hp->head_dim == 64 ? 0 : hp->head_dim == 96 ? 1 : 2;
-    KernelT kern = di == 0 ? decode_mega_kernel<64> : di == 1 ? decode_mega_kernel<96> : decode_mega_kernel<128>;
-    static size_t attr_set_tab[64][3] = {};            // per device (cudaFuncSetAttribute is per device), per kernel variant
+    const bool tr = hp->trace != nullptr;
+    const int di = (hp->head_dim == 64 ? 0 : hp->head_dim == 96 ? 1 : 2) + (tr ? 3 : 0);
+    static const KernelT kerns[6] = {decode_mega_kernel<64, false>, decode_mega_kernel<96, false>, decode_mega_kernel<128, false>,
+                                     decode_mega_kernel<64, true>,  decode_mega_kernel<96, true>,  decode_mega_kernel<128, true>};
+    KernelT kern = kerns[di];
+    static size_t attr_set_tab[64][6] = {};            // per device (cudaFuncSetAttribute is per device), per kernel variant
     int dev = 0;
     cudaGetDevice(&dev);
     size_t* attr_set = attr_set_tab[dev & 63];
