@@ -364,7 +364,7 @@ def run_gvl_arm(args):
             "decode": {"bound": "hbm", "ms_per_step": dec_step_ms, "bytes_per_step": dec_bytes,
                        "achieved_gbs": dec_bytes / (dec_step_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm"],
                        "frac": dec_bytes / (dec_step_ms * 1e-3) / 1e9 / pk["hbm"],
-                       "traffic_bytes_per_step_ncu": 8.88e9,   # dram__bytes_read of one captured launch / its 8 steps (profiles/r2_decode_mega_final_ncu_metrics.csv)
+                       "traffic_bytes_per_step_ncu": 8.86e9,   # dram__bytes_read of one captured launch / its 8 steps (profiles/r2_decode_mega_final_ncu_metrics.csv)
                        "kernel": "gvl::decode_mega_kernel<96> (one persistent launch per generate call; GVL_DECODE_MEGA=0: per-op chain)"
                                  if os.environ.get("GVL_DECODE_MEGA", "1") != "0" else "per-op chain: gemv3_kernel + decode_attn_kernel (CUDA graph)",
                        "samples_ms_per_step": dec_samples, "ms_per_step_generate_minus_prefill": dec_step_diff_ms,
