@@ -10,21 +10,26 @@
 // (decode_mega_pack: item-major, inside an item [32-k chunk][row][32 k]) so that one item is ONE contiguous 8 KB
 // cp.async.bulk into a consumer warp's ring slot -- tools/probe_stream.cu measured 4.8 TB/s with 1 KB row-wise copies
 // and 7.2 TB/s with >= 4 KB copies on B200 -- and the interleave makes the fragment loads bank-conflict free without
-// padding. The warp multiplies the item with mma.sync.m16n8k16 (A = the activation vector broadcast over the
-// 16 rows, B = the 8 weight rows; k is permuted identically on both operands so every lane feeds its fragments with
-// 128-bit shared-memory loads). That is ~6 warp instructions per KB of weights, so the consumers drain the ring several
-// times faster than HBM fills it: the ring runs near-empty inside a phase and absorbs ~4 us of HBM stream while the
-// consumers sit in a barrier / stage the next activation vector. Items of a CTA are dealt round-robin to its 8 warps
+// padding. The warp multiplies the item with mma.sync.m16n8k16 with the WEIGHTS as the A operand: the 16 bytes a lane reads
+// from an item are its A quad (rows 0-7 = the 8 weight rows with the even bf16 pairs of each 8-k group, rows 8-15 the same rows
+// with the odd pairs), the activation vector is staged pair-permuted as B columns 0 / 1 (gemv_items): one LDS.128 + one LDS.64 per
+// HMMA, ~3 warp instructions per KB of weights, bounded by shared-memory bandwidth at ~3x the HBM rate. Inside a phase the
+// consumers therefore wait for ring items (the work phases stream at the HBM copy peak) and the ring absorbs ~4 us of HBM stream
+// while they sit in a barrier / stage the next activation vector. Items of a CTA are dealt round-robin to its 8 warps
 // (k-split inside the CTA, partial sums reduced through shared memory in a fixed order -> deterministic).
 // Every consumer warp has its own 3-slot ring fed by one lane of the producer warp, which keeps at most `inflight`
 // copies per lane outstanding: 8 x 8 KB x 148 SMs = 9.5 MB in flight is enough for the full HBM rate, while deeper
 // queues (the first version had 28 MB outstanding) only add queueing delay (4+ us measured) to every latency-critical
 // load of the phase boundaries (activation staging, barrier atomics, q/k of the attention phase).
 //
-// Attention phase: the flat (head, token) space is cut into equal contiguous ranges, one per consumer warp of the
-// grid; a warp streams K/V rows (4 lanes per token, 8 tokens per pass, 4 passes of K and V loads in flight) with an
-// online softmax, warps of a CTA merge through shared memory, and the <= G/H + 2 CTA partials per head are merged by
-// every CTA while it stages the o_proj input (no atomics, no extra barrier).
+// Attention phase: every head gets the same number of consumer warps of the grid (37 at 148 SMs x 8 warps / 32 heads) and every
+// warp one contiguous token range of one head (att_split); a warp streams K/V rows through its ring (4 lanes per token, 8 tokens
+// per pass) with an online softmax, warps of a CTA merge through shared memory, and the <= G/H + 2 CTA partials per head are merged
+// by every CTA while it stages the o_proj input (one L2 round trip, no atomics, no extra barrier).
+//
+// Code size matters: the consumer side is ONE loop over the phase descriptors, so every phase function is inlined once (6.4k SASS
+// instructions for D = 96). Spelled out per layer it was 13.1k instructions = 210 KB, thrashed the instruction cache in exactly the
+// latency-critical boundary code and cost 7 % of the step (profiles/r2_decode.md). Tracing lives in a separate TRACE instantiation.
 //
 // Reference semantics per phase: Phi3DecoderLayer / LlamaDecoderLayer with q_len = 1 (modeling_phi3.py:1034-1095,
 // 629-775, 413-445; modeling_llama.py:699-760), lm_head + .float() (modeling_phi3.py:1525-1526), greedy pick of
@@ -316,7 +321,7 @@ __device__ __forceinline__ void stage_x_attn(const MegaPlan& P, const Smem& S, i
                 num.x += w.x * ov[i][s2].x; num.y += w.x * ov[i][s2].y; num.z += w.x * ov[i][s2].z; num.w += w.x * ov[i][s2].w;
             }
             const float inv = den > 0.f ? 1.0f / den : 0.f;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(sx) + (e0 >> 3) * 4 + ((e0 >> 2) & 1);      // x_perm layout, see below
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sx) + (e0 >> 3) * 4 + ((e0 >> 2) & 1);      // x_perm layout (general path below)
             dst[0] = pack_bf16(num.x * inv, num.y * inv);
             dst[2] = pack_bf16(num.z * inv, num.w * inv);
         }
