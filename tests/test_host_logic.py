@@ -145,3 +145,42 @@ def test_build_prompt_matches_reference_templates(gold_dir):
         assert H.build_prompt(e["llm"], e["mode"], e["text"], e["duration"]) == e["prompt"], (e["llm"], e["mode"])
     with pytest.raises(ValueError):
         H.build_prompt("phi3.5", "caption", "x")
+
+
+def test_stacked_rows_have_the_shape_and_padding_of_hf_generate():
+    """CausalLM decodes the rows of a batch independently (each until its own EOS) and `_stack_rows` assembles HF generate's [B, L]:
+    L = the step at which the LAST row hit EOS (or max_new_tokens), finished rows padded (GenerationMixin greedy loop as driven at
+    llava_next_video.py:655-661: next = next * unfinished + pad * (1 - unfinished); stop when every row is finished)."""
+    import types
+    from gvl import model
+    eos, pad, V = 2, 0, 11
+
+    def hf_loop(script, max_new):
+        B = len(script)
+        unfinished = torch.ones(B, dtype=torch.long)
+        cols = []
+        for t in range(max_new):
+            nxt = torch.tensor([script[b][t] for b in range(B)])
+            nxt = nxt * unfinished + pad * (1 - unfinished)
+            cols.append(nxt)
+            unfinished = unfinished * (nxt != eos).long()
+            if unfinished.max() == 0:
+                break
+        return torch.stack(cols, dim=1)
+
+    g = torch.Generator().manual_seed(5)
+    fake = types.SimpleNamespace(device="cpu", vocab=V)
+    for case in range(40):
+        B, max_new = int(torch.randint(1, 5, (1,), generator=g)), int(torch.randint(1, 9, (1,), generator=g))
+        script = [[int(x) for x in torch.randint(1, 6, (max_new,), generator=g)] for _ in range(B)]      # eos = 2 appears often
+        want = hf_loop(script, max_new)
+        outs = []
+        for b in range(B):                                   # what one row's decode returns: its tokens up to and including its EOS
+            row = script[b][:max_new]
+            n = row.index(eos) + 1 if eos in row else len(row)
+            outs.append(torch.tensor(row[:n]))
+        got = model.CausalLM._stack_rows(fake, outs, [None] * B, eos, pad, False)
+        assert got.tolist() == want.tolist(), (case, script)
+    # without an EOS id every row runs to max_new_tokens
+    outs = [torch.tensor([4, 2, 5]), torch.tensor([2, 2, 2])]
+    assert model.CausalLM._stack_rows(fake, outs, [None, None], None, pad, False).tolist() == [[4, 2, 5], [2, 2, 2]]
