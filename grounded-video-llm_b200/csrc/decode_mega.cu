@@ -1060,6 +1060,15 @@ size_t decode_mega_att_ws_bytes(const MegaPlan* p) {
     return (size_t)p->heads * p->att_maxp * (p->head_dim + 4) * sizeof(float);
 }
 
+void decode_mega_attention_split(int ctx, int heads, int n_ctas, int* warps_per_head, int* tokens_per_warp, int* max_partials) {
+    const AttSplit a = att_split(ctx, heads, n_ctas);
+    *warps_per_head = a.wph;
+    *tokens_per_warp = a.lw;
+    int mp = 0;
+    for (int h = 0; h < heads; ++h) mp = max(mp, att_c1(h, a.wph) - att_c0(h, a.wph) + 1);
+    *max_partials = mp;
+}
+
 int decode_mega_launch(const MegaPlan* hp, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
                        long long eos_id, long long pad_id, cudaStream_t s) {
     const size_t smem = (size_t)MG_RING_BYTES + hp->x_bytes + (size_t)hp->part_items * 32;

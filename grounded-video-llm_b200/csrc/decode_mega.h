@@ -63,6 +63,8 @@ int decode_mega_pack(const MegaOp* op, const __nv_bfloat16* W, int ldw, __nv_bfl
 // after all ops are set: picks x_bytes / part_items / att_maxp; false when the step does not fit
 bool decode_mega_finalize(MegaPlan* plan);
 size_t decode_mega_att_ws_bytes(const MegaPlan* plan);
+// host view of the attention-phase split (att_split in decode_mega.cu): warps per head, tokens per warp, partial records per head
+void decode_mega_attention_split(int ctx, int heads, int n_ctas, int* warps_per_head, int* tokens_per_warp, int* max_partials);
 int decode_mega_launch(const MegaPlan* plan_host, const MegaPlan* plan_dev, int n_steps, long long* tokens_out, float* logits_out,
                        long long eos_id, long long pad_id, cudaStream_t s);
 

@@ -544,6 +544,15 @@ int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas
     return GVL_OK;
 }
 
+int gvl_lm_attention_split(int ctx, int heads, int n_ctas, int* warps_per_head, int* tokens_per_warp, int* max_partials, int* capacity) {
+    if (ctx < 1 || heads < 1 || heads > 64 || n_ctas < 1 || n_ctas * 8 < heads || !warps_per_head || !tokens_per_warp || !max_partials ||
+        !capacity)
+        return GVL_ERR_ARG;
+    decode_mega_attention_split(ctx, heads, n_ctas, warps_per_head, tokens_per_warp, max_partials);
+    *capacity = n_ctas / heads + 2;             // MegaPlan::att_maxp (decode_mega_finalize)
+    return GVL_OK;
+}
+
 int gvl_lm_decode_kind(const gvl_lm* lm) { return (lm && lm->use_mega && lm->plan_dev) ? 1 : 0; }
 
 const long long* gvl_lm_first_token(gvl_lm* lm) { return lm ? lm->first_tok : nullptr; }

@@ -105,6 +105,7 @@ _SIGS = {
     "gvl_lm_decode": (c_i, [c_vp, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_first_token": (c_vp, [c_vp]),
     "gvl_lm_decode_kind": (c_i, [c_vp]),
+    "gvl_lm_attention_split": (c_i, [c_i, c_i, c_i] + [ctypes.POINTER(c_i)] * 4),
     "gvl_lm_decode_batch": (c_i, [ctypes.POINTER(c_vp), c_i, c_i, c_vp, c_vp, c_ll, c_ll, c_vp]),
     "gvl_lm_set_next_token": (c_i, [c_vp, c_vp, c_vp]),
     "gvl_lm_set_graph": (c_i, [c_vp, c_i]),

@@ -243,6 +243,13 @@ int gvl_lm_mega_trace(gvl_lm* lm, long long* host_out, int max_ctas, int* n_ctas
 int gvl_lm_decode_batch(gvl_lm* const* lms, int n_seq, int n_steps, long long* tokens_out, float* logits_out, long long eos_id,
                         long long pad_id, void* stream);
 
+/* Host-side view of how the single-kernel decode step splits its attention phase over the grid (no GPU needed; tests and capacity
+ * planning): n_ctas x 8 consumer warps, every head gets warps_per_head of them, warp i of a head works on tokens
+ * [i * tokens_per_warp, min(ctx, (i + 1) * tokens_per_warp)); max_partials = the most CTAs any head spreads over (one partial record
+ * per (head, CTA) in the merge workspace), capacity = the records per head the workspace holds. Phi3FlashAttention2 / Llama attention
+ * with q_len = 1 (modeling_phi3.py:629-775, modeling_llama.py:537-594).                                                              */
+int gvl_lm_attention_split(int ctx, int heads, int n_ctas, int* warps_per_head, int* tokens_per_warp, int* max_partials, int* capacity);
+
 /* which decode step this object runs: 1 = the single persistent kernel (decode_mega.cu), 0 = the per-op chain (CUDA graph).
  * The single kernel is the default whenever the shape fits it; GVL_DECODE_MEGA=0 in the environment at create time selects the chain. */
 int gvl_lm_decode_kind(const gvl_lm* lm);
