@@ -132,13 +132,14 @@ def run_reference_arm(args):
     rb = _ref_sampler()
     cores = os.cpu_count() or 1
     sampler = rb.RefCpuSampler(cores)
-    vals, spent = [], 0.0
+    vals, spent, walls = [], 0.0, []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         sec, detail = sampler.sample()
         spent += time.perf_counter() - t0
         if i >= args.warmup:
             vals.append((sec, detail))
+            walls.append(time.perf_counter() - t0)
         if spent > REF_ARM_BUDGET_S and (vals or i + 1 >= args.warmup):
             if not vals:
                 vals.append((sec, detail))                         # the warm-up alone used the budget: keep its last sample
@@ -157,7 +158,11 @@ def run_reference_arm(args):
            "config": {"workload": "BASELINE configs[1]: Phi-3.5-3.8B grounding inference, 1 clip = 96 frames (12x336^2 + 96x224^2), prefill "
                                   "S=%d + %d greedy tokens" % (S_PREFILL, DECODE_TOKENS),
                       "where": "host CPU, the reference's own modules (oracle/_ref), torch fp32, %d threads" % cores,
-                      "samples_timed": len(vals), "sample_budget_s": REF_ARM_BUDGET_S},
+                      "samples_timed": len(vals), "sample_budget_s": REF_ARM_BUDGET_S,
+                      "wall_s_per_sample": (sum(walls) / len(walls)) if walls else None,
+                      "scaling_of_a_step": "ms_per_step = one bounded sample SCALED to a full clip (units and layers it skips multiplied "
+                                           "back in, cpu_baseline.sample); the wall time one sample takes is wall_s_per_sample, so "
+                                           "steps x ms_per_step is not this run's duration"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sampler.SAMPLE},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "detail_s": vals[-1][1],
